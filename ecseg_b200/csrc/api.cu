@@ -1,0 +1,241 @@
+// C ABI of libecseg_b200.so (include/ecseg_b200.h): context lifetime and the entry points the
+// reference-facing Python shim binds.  No exceptions cross this boundary.
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+namespace ecseg {
+int unet_set_debug(ecseg_ctx* ctx, int stop_after, int tc_pitch, int tc_desc_mode, int tc_ntile_max);
+int fe_zero_counters(ecseg_ctx* ctx, cudaStream_t st);
+}
+
+using namespace ecseg;
+
+#define API_GUARD(ctx)                                  \
+  if (!(ctx)) return ECSEG_E_INVALID;                   \
+  if (cudaSetDevice((ctx)->device) != cudaSuccess) {    \
+    (ctx)->err = "cudaSetDevice failed";                \
+    return ECSEG_E_CUDA;                                \
+  }
+
+static int check_hw(ecseg_ctx* ctx, int h, int w, const char* who) {
+  if (h < 1 || w < 1 || (size_t)h * w > ctx->max_px) {
+    ctx->err = std::string(who) + ": image exceeds the context's max_h x max_w";
+    return ECSEG_E_INVALID;
+  }
+  return ECSEG_OK;
+}
+
+extern "C" {
+
+const char* ecseg_version(void) { return "ecseg_b200 0.1 (sm_100a)"; }
+
+int ecseg_ctx_create(ecseg_ctx** out, int device, int max_h, int max_w, int max_tiles) {
+  if (!out || max_h < 1 || max_w < 1 || max_tiles < 0) return ECSEG_E_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return ECSEG_E_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return ECSEG_E_CUDA;
+  ecseg_ctx* ctx = new (std::nothrow) ecseg_ctx();
+  if (!ctx) return ECSEG_E_INVALID;
+  ctx->device = device;
+  ctx->max_h = max_h; ctx->max_w = max_w; ctx->max_tiles = max_tiles;
+  ctx->max_px = (size_t)max_h * max_w;
+  const size_t P = ctx->max_px;
+  bool ok = true;
+  auto A = [&](void** p, size_t bytes) { if (ok && cudaMalloc(p, bytes) != cudaSuccess) ok = false; };
+  A((void**)&ctx->L, P * 4); A((void**)&ctx->area, P * 4); A((void**)&ctx->sum_y, P * 8); A((void**)&ctx->sum_x, P * 8);
+  A((void**)&ctx->flag, P * 4); A((void**)&ctx->tmp_a, P); A((void**)&ctx->tmp_b, P);
+  A((void**)&ctx->chrom_cy, (P / 4 + 16) * 8); A((void**)&ctx->chrom_cx, (P / 4 + 16) * 8);
+  A((void**)&ctx->nuc_roots, (P / 4 + 16) * 4);
+  A((void**)&ctx->counters, sizeof(Counters));
+  A((void**)&ctx->img_in, P * 8); A((void**)&ctx->pre, P); A((void**)&ctx->dapi, P); A((void**)&ctx->labels, P);
+  A((void**)&ctx->d_n_ec, 8); A((void**)&ctx->d_ec_px, 8);
+  if (ok && cudaMemset(ctx->counters, 0, sizeof(Counters)) != cudaSuccess) ok = false;
+  for (auto& e : ctx->ev) if (ok && cudaEventCreate(&e) != cudaSuccess) ok = false;
+  if (ok && unet_create(ctx) != ECSEG_OK) ok = false;
+  if (!ok) { ecseg_ctx_destroy(ctx); return ECSEG_E_CUDA; }
+  *out = ctx;
+  return ECSEG_OK;
+}
+
+void ecseg_ctx_destroy(ecseg_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  unet_destroy(ctx);
+  void* ptrs[] = {ctx->L, ctx->area, ctx->sum_y, ctx->sum_x, ctx->flag, ctx->tmp_a, ctx->tmp_b, ctx->chrom_cy,
+                  ctx->chrom_cx, ctx->nuc_roots, ctx->counters, ctx->img_in, ctx->pre, ctx->dapi, ctx->labels,
+                  ctx->d_n_ec, ctx->d_ec_px};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  delete ctx;
+}
+
+const char* ecseg_last_error(ecseg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int64_t ecseg_launch_count(ecseg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ecseg_load_weights(ecseg_ctx* ctx, const float* blob, size_t n_floats, int precision) {
+  API_GUARD(ctx);
+  if (!blob) { ctx->err = "load_weights: null blob"; return ECSEG_E_INVALID; }
+  ECSEG_CUDA(cudaDeviceSynchronize());
+  return unet_load_weights(ctx, blob, n_floats, precision);
+}
+
+int ecseg_tile_grid(int h, int w, int* n_tiles, int* n_rows, int* n_cols, int32_t* pos) {
+  if (h < kTile || w < kTile) return ECSEG_E_INVALID;   // the reference cannot tile smaller images
+  TileGrid g = make_grid(h, w);
+  if (n_tiles) *n_tiles = g.n();
+  if (n_rows) *n_rows = g.nr;
+  if (n_cols) *n_cols = g.nc;
+  if (pos)
+    for (int k = 0; k < g.n(); ++k) { pos[2 * k] = g.start_r(k % g.nr); pos[2 * k + 1] = g.start_c(k / g.nr); }
+  return ECSEG_OK;
+}
+
+int ecseg_preprocess(ecseg_ctx* ctx, const void* d_img, int h, int w, int ch, int bytes_per_sample, uint8_t* d_pre,
+                     uint8_t* d_dapi, void* stream) {
+  API_GUARD(ctx);
+  ECSEG_TRY(check_hw(ctx, h, w, "ecseg_preprocess"));
+  return fe_preprocess(ctx, d_img, h, w, ch, bytes_per_sample, d_pre, d_dapi, (cudaStream_t)stream);
+}
+
+int ecseg_tile(ecseg_ctx* ctx, const uint8_t* d_pre, int h, int w, uint8_t* d_tiles, void* stream) {
+  API_GUARD(ctx);
+  return fe_tile(ctx, d_pre, h, w, d_tiles, (cudaStream_t)stream);
+}
+
+int ecseg_unet_forward(ecseg_ctx* ctx, const uint8_t* d_tiles, int n, float* d_probs, float* d_logits, void* stream) {
+  API_GUARD(ctx);
+  if (!d_tiles) { ctx->err = "ecseg_unet_forward: null tiles"; return ECSEG_E_INVALID; }
+  return unet_forward(ctx, d_tiles, nullptr, nullptr, n, d_probs, d_logits, nullptr, (cudaStream_t)stream);
+}
+
+int ecseg_stitch_argmax(ecseg_ctx* ctx, const float* d_probs, int h, int w, uint8_t* d_labels, void* stream) {
+  API_GUARD(ctx);
+  cudaStream_t st = (cudaStream_t)stream;
+  ECSEG_TRY(fe_zero_counters(ctx, st));
+  ECSEG_TRY(fe_stitch_argmax(ctx, d_probs, h, w, d_labels, st));
+  // img_as_ubyte raises on values outside [-1, 1] (reference src/utils.py:117): surface it.
+  int range_error = 0;
+  ECSEG_CUDA(cudaMemcpyAsync(&range_error, &ctx->counters->range_error, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ECSEG_CUDA(cudaStreamSynchronize(st));
+  if (range_error) { ctx->err = "Images of type float must be between -1 and 1."; return ECSEG_E_RANGE; }
+  return ECSEG_OK;
+}
+
+int ecseg_postprocess(ecseg_ctx* ctx, uint8_t* d_labels, int h, int w, int flags, int32_t* d_n_ec, int64_t* d_ec_px,
+                      void* stream) {
+  API_GUARD(ctx);
+  return pp_postprocess(ctx, d_labels, h, w, flags, d_n_ec, d_ec_px, (cudaStream_t)stream);
+}
+
+int ecseg_count_cc(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w, int32_t* d_n, int64_t* d_px, void* stream) {
+  API_GUARD(ctx);
+  ECSEG_TRY(check_hw(ctx, h, w, "ecseg_count_cc"));
+  return pp_count_cc(ctx, d_mask, h, w, d_n, d_px, (cudaStream_t)stream);
+}
+
+int ecseg_fill_holes(ecseg_ctx* ctx, uint8_t* d_labels, int h, int w, int class_id, void* stream) {
+  API_GUARD(ctx);
+  ECSEG_TRY(check_hw(ctx, h, w, "ecseg_fill_holes"));
+  return pp_fill_holes(ctx, d_labels, h, w, class_id, (cudaStream_t)stream);
+}
+
+int ecseg_size_thresh(ecseg_ctx* ctx, uint8_t* d_labels, int h, int w, void* stream) {
+  API_GUARD(ctx);
+  ECSEG_TRY(check_hw(ctx, h, w, "ecseg_size_thresh"));
+  return pp_size_thresh(ctx, d_labels, h, w, (cudaStream_t)stream);
+}
+
+int ecseg_merge_comp(ecseg_ctx* ctx, uint8_t* d_labels, int h, int w, int class_id, void* stream) {
+  API_GUARD(ctx);
+  ECSEG_TRY(check_hw(ctx, h, w, "ecseg_merge_comp"));
+  return pp_merge_comp(ctx, d_labels, h, w, class_id, (cudaStream_t)stream);
+}
+
+int ecseg_label(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w, int connectivity, int32_t* d_out, void* stream) {
+  API_GUARD(ctx);
+  ECSEG_TRY(check_hw(ctx, h, w, "ecseg_label"));
+  return pp_label(ctx, d_mask, h, w, connectivity, d_out, (cudaStream_t)stream);
+}
+
+int ecseg_segment_image(ecseg_ctx* ctx, const void* d_img, int h, int w, int ch, int bytes_per_sample, uint8_t* d_dapi,
+                        uint8_t* d_labels, int32_t* d_n_ec, int64_t* d_ec_px, int flags, void* stream) {
+  API_GUARD(ctx);
+  cudaStream_t st = (cudaStream_t)stream;
+  ECSEG_TRY(check_hw(ctx, h, w, "ecseg_segment_image"));
+  if (!d_labels) { ctx->err = "ecseg_segment_image: null labels"; return ECSEG_E_INVALID; }
+  if (h < kTile || w < kTile) { ctx->err = "ecseg_segment_image: need h,w >= 256"; return ECSEG_E_INVALID; }
+  TileGrid g = make_grid(h, w);
+  if (g.n() > ctx->max_tiles) { ctx->err = "ecseg_segment_image: tile count exceeds the context's max_tiles"; return ECSEG_E_INVALID; }
+  ECSEG_CUDA(cudaEventRecord(ctx->ev[0], st));
+  ECSEG_TRY(fe_preprocess(ctx, d_img, h, w, ch, bytes_per_sample, ctx->pre, d_dapi, st));
+  ECSEG_CUDA(cudaEventRecord(ctx->ev[1], st));
+  // tiles are gathered inside conv1-1, the stitch is fused into the head's epilogue
+  ECSEG_TRY(unet_forward(ctx, nullptr, ctx->pre, &g, g.n(), nullptr, nullptr, d_labels, st));
+  ECSEG_CUDA(cudaEventRecord(ctx->ev[2], st));
+  ECSEG_CUDA(cudaEventRecord(ctx->ev[3], st));
+  ECSEG_TRY(pp_postprocess(ctx, d_labels, h, w, flags, d_n_ec, d_ec_px, st));
+  ECSEG_CUDA(cudaEventRecord(ctx->ev[4], st));
+  ctx->ev_valid = true;
+  return ECSEG_OK;
+}
+
+int ecseg_segment_image_host(ecseg_ctx* ctx, const void* h_img, int h, int w, int ch, int bytes_per_sample,
+                             uint8_t* h_dapi, uint8_t* h_labels, int32_t* n_ec, int64_t* ec_px, int flags) {
+  API_GUARD(ctx);
+  ECSEG_TRY(check_hw(ctx, h, w, "ecseg_segment_image_host"));
+  if (!h_img || !h_labels || (ch != 1 && ch != 3 && ch != 4) || (bytes_per_sample != 1 && bytes_per_sample != 2)) {
+    ctx->err = "ecseg_segment_image_host: bad arguments";
+    return ECSEG_E_INVALID;
+  }
+  cudaStream_t st = 0;
+  const size_t n_px = (size_t)h * w;
+  ECSEG_CUDA(cudaMemcpyAsync(ctx->img_in, h_img, n_px * ch * bytes_per_sample, cudaMemcpyHostToDevice, st));
+  ECSEG_TRY(ecseg_segment_image(ctx, ctx->img_in, h, w, ch, bytes_per_sample, h_dapi ? ctx->dapi : nullptr, ctx->labels,
+                                ctx->d_n_ec, ctx->d_ec_px, flags, st));
+  ECSEG_CUDA(cudaMemcpyAsync(h_labels, ctx->labels, n_px, cudaMemcpyDeviceToHost, st));
+  if (h_dapi) ECSEG_CUDA(cudaMemcpyAsync(h_dapi, ctx->dapi, n_px, cudaMemcpyDeviceToHost, st));
+  int32_t n = 0; int64_t px = 0; int dev_err = 0;
+  ECSEG_CUDA(cudaMemcpyAsync(&n, ctx->d_n_ec, 4, cudaMemcpyDeviceToHost, st));
+  ECSEG_CUDA(cudaMemcpyAsync(&px, ctx->d_ec_px, 8, cudaMemcpyDeviceToHost, st));
+  ECSEG_CUDA(cudaMemcpyAsync(&dev_err, &ctx->counters->device_error, 4, cudaMemcpyDeviceToHost, st));
+  ECSEG_CUDA(cudaStreamSynchronize(st));
+  if (dev_err) { ctx->err = "tcgen05 pipeline watchdog fired (code " + std::to_string(dev_err) + ")"; return ECSEG_E_DEVICE; }
+  if (n_ec) *n_ec = n;
+  if (ec_px) *ec_px = px;
+  return ECSEG_OK;
+}
+
+int ecseg_debug_layer_output(ecseg_ctx* ctx, int layer, int n, float* d_out, void* stream) {
+  API_GUARD(ctx);
+  return unet_debug_layer(ctx, layer, n, d_out, (cudaStream_t)stream);
+}
+
+int ecseg_debug_set(ecseg_ctx* ctx, int stop_after_layer, int tc_pitch, int tc_desc_mode, int tc_ntile_max) {
+  API_GUARD(ctx);
+  return unet_set_debug(ctx, stop_after_layer, tc_pitch, tc_desc_mode, tc_ntile_max);
+}
+
+int ecseg_device_error(ecseg_ctx* ctx, int* code) {
+  API_GUARD(ctx);
+  ECSEG_CUDA(cudaDeviceSynchronize());
+  ECSEG_CUDA(cudaMemcpy(code, &ctx->counters->device_error, 4, cudaMemcpyDeviceToHost));
+  return ECSEG_OK;
+}
+
+int ecseg_last_stage_ms(ecseg_ctx* ctx, float ms[4]) {
+  API_GUARD(ctx);
+  if (!ctx->ev_valid || !ms) { if (ctx) ctx->err = "last_stage_ms: no segment_image call yet"; return ECSEG_E_STATE; }
+  ECSEG_CUDA(cudaEventSynchronize(ctx->ev[4]));
+  ECSEG_CUDA(cudaEventElapsedTime(&ms[0], ctx->ev[0], ctx->ev[1]));
+  ECSEG_CUDA(cudaEventElapsedTime(&ms[1], ctx->ev[1], ctx->ev[2]));
+  ECSEG_CUDA(cudaEventElapsedTime(&ms[2], ctx->ev[2], ctx->ev[3]));
+  ECSEG_CUDA(cudaEventElapsedTime(&ms[3], ctx->ev[3], ctx->ev[4]));
+  return ECSEG_OK;
+}
+
+}  // extern "C"

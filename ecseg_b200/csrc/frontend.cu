@@ -1,0 +1,175 @@
+// Tile / stitch front end of the metaseg path (HBM-bound byte kernels).
+//
+//   fe_preprocess     <- image_tools.meta_preprocess + u16_to_u8   (reference src/image_tools.py:86-101)
+//   fe_tile           <- image_tools.im2patches_overlap            (reference src/image_tools.py:148-186)
+//   fe_stitch_argmax  <- image_tools.patches2im_overlap            (reference src/image_tools.py:188-252)
+//                        + skimage.img_as_ubyte + np.argmax        (reference src/utils.py:117-118)
+#include "common.cuh"
+#include "stitch.cuh"
+
+namespace ecseg {
+
+// ------------------------------------------------------------------------------------------------
+// pre-processing
+// ------------------------------------------------------------------------------------------------
+__global__ void k_zero_counters(Counters* c) {
+  unsigned int* p = reinterpret_cast<unsigned int*>(c);
+  for (int i = threadIdx.x; i < (int)(sizeof(Counters) / 4); i += blockDim.x) p[i] = 0;
+}
+
+int fe_zero_counters(ecseg_ctx* ctx, cudaStream_t st) {
+  k_zero_counters<<<1, 128, 0, st>>>(ctx->counters);
+  ECSEG_CHECK_LAUNCH();
+  return ECSEG_OK;
+}
+
+// u16 -> u8 exactly like cv2.convertScaleAbs(alpha=255/65535): rint(x*alpha), half to even.
+__device__ __forceinline__ uint8_t scale_u16(unsigned int v) {
+  double r = __dmul_rn((double)v, 255.0 / 65535.0);
+  int q = __double2int_rn(r);
+  return (uint8_t)min(max(q, 0), 255);
+}
+
+// Pass 1: channel pick (channel 2 of colour images, image_tools.py:88-89), u16->u8, 256-bin histogram.
+template <typename T>
+__global__ void k_pre_convert_hist(const T* __restrict__ img, int n_px, int ch, uint8_t* __restrict__ pre,
+                                   Counters* __restrict__ cnt) {
+  __shared__ unsigned int sh[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const int pick = ch > 1 ? 2 : 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += gridDim.x * blockDim.x) {
+    unsigned int v = img[(size_t)i * ch + pick];
+    uint8_t b = sizeof(T) == 2 ? scale_u16(v) : (uint8_t)v;
+    pre[i] = b;
+    atomicAdd(&sh[b], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    if (sh[i]) atomicAdd(&cnt->hist[i], sh[i]);
+}
+
+// Otsu threshold as OpenCV's getThreshVal_Otsu_8u computes it (double precision, first maximum),
+// then the reference's polarity test  sum(px > T) > 0.5*H*W  (image_tools.py:91-95).
+// One thread: 256 iterations of scalar fp64, no FMA contraction (explicit _rn intrinsics) so the
+// result is bit-identical to the CPU evaluation order.
+__global__ void k_otsu(Counters* cnt, int n_px) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double scale = __ddiv_rn(1.0, (double)n_px);
+  double mu = 0.0;
+  for (int i = 0; i < 256; ++i) mu = __dadd_rn(mu, __dmul_rn((double)i, (double)cnt->hist[i]));
+  mu = __dmul_rn(mu, scale);
+  double mu1 = 0.0, q1 = 0.0, max_sigma = 0.0;
+  int max_val = 0;
+  const double eps = 1.1920928955078125e-07;  // FLT_EPSILON
+  for (int i = 0; i < 256; ++i) {
+    double p_i = __dmul_rn((double)cnt->hist[i], scale);
+    mu1 = __dmul_rn(mu1, q1);
+    q1 = __dadd_rn(q1, p_i);
+    double q2 = __dsub_rn(1.0, q1);
+    if (fmin(q1, q2) < eps || fmax(q1, q2) > 1.0 - eps) continue;
+    mu1 = __ddiv_rn(__dadd_rn(mu1, __dmul_rn((double)i, p_i)), q1);
+    double mu2 = __ddiv_rn(__dsub_rn(mu, __dmul_rn(q1, mu1)), q2);
+    double d = __dsub_rn(mu1, mu2);
+    double sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), d), d);
+    if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
+  }
+  unsigned long long above = 0;
+  for (int i = max_val + 1; i < 256; ++i) above += cnt->hist[i];
+  cnt->otsu_threshold = max_val;
+  cnt->n_above = above;
+  cnt->flip = ((double)above > (double)n_px * 0.5) ? 1 : 0;
+}
+
+// Pass 2: apply the polarity flip (~img) and emit the dapi/ artefact (255 - pre, utils.py:112).
+__global__ void k_pre_apply(uint8_t* __restrict__ pre, uint8_t* __restrict__ dapi, int n_px,
+                            const Counters* __restrict__ cnt) {
+  const int flip = cnt->flip;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += gridDim.x * blockDim.x) {
+    uint8_t v = pre[i];
+    if (flip) { v = 255 - v; pre[i] = v; }
+    if (dapi) dapi[i] = 255 - v;
+  }
+}
+
+int fe_preprocess(ecseg_ctx* ctx, const void* d_img, int h, int w, int ch, int bps, uint8_t* d_pre,
+                  uint8_t* d_dapi, cudaStream_t st) {
+  if (!d_img || !d_pre || h < kTile || w < kTile || (ch != 1 && ch != 3 && ch != 4) || (bps != 1 && bps != 2)) {
+    ctx->err = "ecseg_preprocess: need h,w >= 256, ch in {1,3,4}, 1 or 2 bytes per sample";
+    return ECSEG_E_INVALID;
+  }
+  const int n_px = h * w;
+  k_zero_counters<<<1, 128, 0, st>>>(ctx->counters);
+  ECSEG_CHECK_LAUNCH();
+  const int blocks = min(cdiv(n_px, 256 * 8), 148 * 8);
+  if (bps == 1)
+    k_pre_convert_hist<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t*)d_img, n_px, ch, d_pre, ctx->counters);
+  else
+    k_pre_convert_hist<uint16_t><<<blocks, 256, 0, st>>>((const uint16_t*)d_img, n_px, ch, d_pre, ctx->counters);
+  ECSEG_CHECK_LAUNCH();
+  k_otsu<<<1, 32, 0, st>>>(ctx->counters, n_px);
+  ECSEG_CHECK_LAUNCH();
+  k_pre_apply<<<blocks, 256, 0, st>>>(d_pre, d_dapi, n_px, ctx->counters);
+  ECSEG_CHECK_LAUNCH();
+  return ECSEG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tiling
+// ------------------------------------------------------------------------------------------------
+// One block per (tile, 16-row band); 16-byte vector copies where the source is aligned.
+__global__ void k_tile_gather(const uint8_t* __restrict__ pre, TileGrid g, uint8_t* __restrict__ tiles) {
+  const int k = blockIdx.x;                 // tile index: row start varies fastest (meshgrid order)
+  const int ri = k % g.nr, ci = k / g.nr;
+  const int r0 = g.start_r(ri), c0 = g.start_c(ci);
+  const int band = blockIdx.y * 16;
+  for (int t = threadIdx.x; t < 16 * kTile; t += blockDim.x) {
+    int y = band + t / kTile, x = t % kTile;
+    tiles[((size_t)k * kTile + y) * kTile + x] = pre[(size_t)(r0 + y) * g.w + c0 + x];
+  }
+}
+
+int fe_tile(ecseg_ctx* ctx, const uint8_t* d_pre, int h, int w, uint8_t* d_tiles, cudaStream_t st) {
+  if (!d_pre || !d_tiles || h < kTile || w < kTile) {
+    ctx->err = "ecseg_tile: need h,w >= 256";
+    return ECSEG_E_INVALID;
+  }
+  TileGrid g = make_grid(h, w);
+  k_tile_gather<<<dim3(g.n(), kTile / 16), 256, 0, st>>>(d_pre, g, d_tiles);
+  ECSEG_CHECK_LAUNCH();
+  return ECSEG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stitch + quantise + argmax
+// ------------------------------------------------------------------------------------------------
+__global__ void k_stitch_argmax(const float4* __restrict__ probs, TileGrid g, uint8_t* __restrict__ labels,
+                                Counters* __restrict__ cnt) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= g.w) return;
+  uint8_t out = 0;
+  if (!stitch_hole(g, y, x)) {
+    const int ri = axis_owner(y, g.h, g.nr, g.rem_r), ci = axis_owner(x, g.w, g.nc, g.rem_c);
+    const int ty = y - g.start_r(ri), tx = x - g.start_c(ci);
+    const int k = ci * g.nr + ri;
+    float4 p = probs[((size_t)k * kTile + ty) * kTile + tx];
+    int err = 0;
+    out = (uint8_t)quantised_argmax(p.x, p.y, p.z, p.w, &err);
+    if (err) cnt->range_error = 1;
+  }
+  labels[(size_t)y * g.w + x] = out;
+}
+
+int fe_stitch_argmax(ecseg_ctx* ctx, const float* d_probs, int h, int w, uint8_t* d_labels, cudaStream_t st) {
+  if (!d_probs || !d_labels || h < kTile || w < kTile) {
+    ctx->err = "ecseg_stitch_argmax: need h,w >= 256";
+    return ECSEG_E_INVALID;
+  }
+  TileGrid g = make_grid(h, w);
+  k_stitch_argmax<<<dim3(cdiv(w, 256), h), 256, 0, st>>>((const float4*)d_probs, g, d_labels, ctx->counters);
+  ECSEG_CHECK_LAUNCH();
+  return ECSEG_OK;
+}
+
+}  // namespace ecseg

@@ -1,0 +1,515 @@
+// Post-processing of the 4-class label map: union-find connected-component labelling with
+// per-component reductions, 3x3-cross morphology and the rule kernels of meta_inference.
+//
+//   pp_postprocess  <- image_tools.meta_inference (reference src/image_tools.py:15-84)
+//                      + image_tools.count_cc(I==3) (src/image_tools.py:114-119, src/metaseg.py:46)
+//   pp_fill_holes   <- nested fill_holes  (src/image_tools.py:36-39)
+//   pp_size_thresh  <- nested size_thresh (src/image_tools.py:41-59)
+//   pp_merge_comp   <- nested merge_comp  (src/image_tools.py:18-33)
+//   pp_count_cc     <- image_tools.count_cc
+//
+// Labelling scheme: every foreground pixel ends up with L[i] = smallest linear index of its
+// component (the component's first pixel in raster order), background -1.  That root index is
+// also the slot of the per-component statistics, and raster order of roots is exactly the label
+// order of scipy.ndimage.label / skimage.measure.label, which the merge_comp "skip the last
+// component" quirk depends on.
+//
+// All kernels are HBM-bound byte/int kernels: one thread per pixel, a warp covers 32 consecutive
+// pixels of one image row so that horizontal runs are resolved with one ballot (no memory
+// traffic), and only run heads issue union operations.
+#include "common.cuh"
+
+namespace ecseg {
+
+enum KeyMode {
+  KEY_CLASS = 0,      // key = class value (components of equal class; 0 is background)
+  KEY_EQ = 1,         // key = (v == c)
+  KEY_NE = 2,         // key = (v != c)
+  KEY_NZ_EXCEPT = 3,  // key = (v != 0 && v != c)
+  KEY_NONZERO = 4     // key = (v != 0)
+};
+
+__device__ __forceinline__ int key_of(uint8_t v, int mode, int c) {
+  switch (mode) {
+    case KEY_CLASS: return v;
+    case KEY_EQ: return v == c;
+    case KEY_NE: return v != c;
+    case KEY_NZ_EXCEPT: return v != 0 && v != c;
+    default: return v != 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// union-find primitives (root = minimum index; links always point to a smaller index)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(const int32_t* L, int a) {
+  int p = __ldcg(L + a);
+  while (p != a) { a = p; p = __ldcg(L + a); }
+  return a;
+}
+
+__device__ __forceinline__ void uf_union(int32_t* L, int a, int b) {
+  bool done = false;
+  while (!done) {
+    a = uf_find(L, a);
+    b = uf_find(L, b);
+    if (a < b) {
+      int old = atomicMin(L + b, a);
+      done = (old == b);
+      b = old;
+    } else if (b < a) {
+      int old = atomicMin(L + a, b);
+      done = (old == a);
+      a = old;
+    } else {
+      done = true;
+    }
+  }
+}
+
+#define PIXEL_XY()                                              \
+  const int x = blockIdx.x * 32 + threadIdx.x;                  \
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;          \
+  if (y >= h) return; /* warp-uniform */
+
+static inline dim3 px_grid(int h, int w) { return dim3(cdiv(w, 32), cdiv(h, 8)); }
+static inline dim3 px_block() { return dim3(32, 8); }
+
+__global__ void k_pp_zero(Counters* c) {
+  if (threadIdx.x < 4) { c->ncomp[threadIdx.x] = 0; c->npix[threadIdx.x] = 0; }
+  if (threadIdx.x == 0) { c->n_chrom = 0; c->n_nuc = 0; c->last_root = -1; }
+}
+
+// Pass 1: L[i] = index of the head of pixel i's horizontal run inside its 32-pixel segment.
+__global__ void k_ccl_init(const uint8_t* __restrict__ cls, int h, int w, int mode, int c, int32_t* __restrict__ L) {
+  PIXEL_XY();
+  const bool in = x < w;
+  const int k = in ? key_of(cls[(size_t)y * w + x], mode, c) : 0;
+  const int kl = __shfl_up_sync(0xffffffffu, k, 1);
+  const bool same = threadIdx.x > 0 && kl == k;
+  const unsigned heads = ~__ballot_sync(0xffffffffu, same);
+  if (!in) return;
+  const unsigned m = heads & (0xffffffffu >> (31 - threadIdx.x));
+  const int head = 31 - __clz(m);
+  L[(size_t)y * w + x] = k ? (y * w + blockIdx.x * 32 + head) : -1;
+}
+
+// Pass 2: union across segment boundaries and with the row above; only run heads (and pixels
+// whose upper-left neighbour differs) issue a union, everything else is implied by the run links.
+__global__ void k_ccl_merge(const uint8_t* __restrict__ cls, int h, int w, int mode, int c, int conn8,
+                            int32_t* __restrict__ L) {
+  PIXEL_XY();
+  if (x >= w) return;
+  const int i = y * w + x;
+  const int k = key_of(cls[i], mode, c);
+  if (!k) return;
+  const bool left_same = x > 0 && key_of(cls[i - 1], mode, c) == k;
+  if (threadIdx.x == 0 && left_same) uf_union(L, i, i - 1);
+  if (y == 0) return;
+  const bool run_head = threadIdx.x == 0 || !left_same;
+  const bool up_same = key_of(cls[i - w], mode, c) == k;
+  const bool nw_same = x > 0 && key_of(cls[i - w - 1], mode, c) == k;
+  if (up_same) {
+    if (run_head || !nw_same) uf_union(L, i, i - w);
+  } else if (conn8) {
+    if (run_head && nw_same) uf_union(L, i, i - w - 1);
+    if (x < w - 1) {
+      const bool right_same = key_of(cls[i + 1], mode, c) == k;
+      if (!right_same && key_of(cls[i - w + 1], mode, c) == k) uf_union(L, i, i - w + 1);
+    }
+  }
+}
+
+// Pass 3: point every pixel at its root; roots reset their statistics slot and are counted.
+__global__ void k_ccl_flatten(const uint8_t* __restrict__ cls, int h, int w, int mode, int c, int32_t* __restrict__ L,
+                              int32_t* __restrict__ area, unsigned long long* __restrict__ sy,
+                              unsigned long long* __restrict__ sx, int32_t* __restrict__ flag,
+                              Counters* __restrict__ cnt) {
+  __shared__ unsigned int s_fg;
+  if (threadIdx.x == 0 && threadIdx.y == 0) s_fg = 0;
+  __syncthreads();
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  bool fg = false;
+  if (y < h && x < w) {
+    const int i = y * w + x;
+    if (L[i] >= 0) {
+      fg = true;
+      const int r = uf_find(L, i);
+      L[i] = r;
+      if (r == i) {
+        area[i] = 0; sy[i] = 0ull; sx[i] = 0ull; flag[i] = 0;
+        atomicAdd(&cnt->ncomp[key_of(cls[i], mode, c) & 3], 1);
+        atomicMax(&cnt->last_root, i);
+      }
+    }
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, fg);
+  if (threadIdx.x == 0 && b) atomicAdd(&s_fg, (unsigned)__popc(b));
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0 && s_fg) atomicAdd(&cnt->npix[0], (unsigned long long)s_fg);
+}
+
+// Per-component area (and optionally coordinate sums), warp-aggregated by root before the atomics;
+// per-class pixel totals are block-reduced.
+__global__ void k_ccl_accumulate(const uint8_t* __restrict__ cls, int h, int w, const int32_t* __restrict__ L,
+                                 int32_t* __restrict__ area, unsigned long long* __restrict__ sy,
+                                 unsigned long long* __restrict__ sx, int want_centroid, Counters* __restrict__ cnt) {
+  __shared__ unsigned int s_cls[4];
+  if (threadIdx.y == 0 && threadIdx.x < 4) s_cls[threadIdx.x] = 0;
+  __syncthreads();
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  int r = -1, v = 0;
+  if (y < h && x < w) { r = L[y * w + x]; v = cls[y * w + x]; }
+  const bool valid = r >= 0;
+  const unsigned act = __ballot_sync(0xffffffffu, valid);
+  if (valid) {
+    const unsigned peers = __match_any_sync(act, r);
+    if ((int)threadIdx.x == __ffs(peers) - 1) {
+      const int n = __popc(peers);
+      atomicAdd(area + r, n);
+      if (want_centroid) {
+        unsigned m = peers;
+        unsigned long long sxs = 0;
+        while (m) { sxs += (unsigned)(__ffs(m) - 1); m &= m - 1; }
+        atomicAdd(sy + r, (unsigned long long)n * (unsigned)y);
+        atomicAdd(sx + r, sxs + (unsigned long long)n * (unsigned)(blockIdx.x * 32));
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 1; k < 4; ++k) {
+    const unsigned b = __ballot_sync(0xffffffffu, v == k);
+    if (threadIdx.x == 0 && b) atomicAdd(&s_cls[k], (unsigned)__popc(b));
+  }
+  __syncthreads();
+  if (threadIdx.y == 0 && threadIdx.x > 0 && threadIdx.x < 4 && s_cls[threadIdx.x])
+    atomicAdd(&cnt->npix[threadIdx.x], (unsigned long long)s_cls[threadIdx.x]);
+}
+
+static int ccl_run(ecseg_ctx* ctx, const uint8_t* cls, int h, int w, int mode, int c, int conn8, cudaStream_t st) {
+  k_pp_zero<<<1, 32, 0, st>>>(ctx->counters);
+  ECSEG_CHECK_LAUNCH();
+  k_ccl_init<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, mode, c, ctx->L);
+  ECSEG_CHECK_LAUNCH();
+  k_ccl_merge<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, mode, c, conn8, ctx->L);
+  ECSEG_CHECK_LAUNCH();
+  k_ccl_flatten<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, mode, c, ctx->L, ctx->area, ctx->sum_y,
+                                                      ctx->sum_x, ctx->flag, ctx->counters);
+  ECSEG_CHECK_LAUNCH();
+  return ECSEG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fill_holes  (image_tools.py:36-39): complement components that do not touch the image border
+// ------------------------------------------------------------------------------------------------
+__global__ void k_mark_border(const int32_t* __restrict__ L, int h, int w, int32_t* __restrict__ flag) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = 2 * w + 2 * h;
+  if (t >= per) return;
+  int y, x;
+  if (t < w) { y = 0; x = t; }
+  else if (t < 2 * w) { y = h - 1; x = t - w; }
+  else if (t < 2 * w + h) { y = t - 2 * w; x = 0; }
+  else { y = t - 2 * w - h; x = w - 1; }
+  const int r = L[y * w + x];
+  if (r >= 0) flag[r] = 1;
+}
+
+__global__ void k_fill_apply(uint8_t* __restrict__ cls, int h, int w, const int32_t* __restrict__ L,
+                             const int32_t* __restrict__ flag, int c) {
+  PIXEL_XY();
+  if (x >= w) return;
+  const int i = y * w + x;
+  const int r = L[i];
+  if (r >= 0 && !flag[r]) cls[i] = (uint8_t)c;
+}
+
+int pp_fill_holes(ecseg_ctx* ctx, uint8_t* cls, int h, int w, int c, cudaStream_t st) {
+  ECSEG_TRY(ccl_run(ctx, cls, h, w, KEY_NE, c, /*conn8=*/0, st));
+  k_mark_border<<<cdiv(2 * (h + w), 256), 256, 0, st>>>(ctx->L, h, w, ctx->flag);
+  ECSEG_CHECK_LAUNCH();
+  k_fill_apply<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, ctx->L, ctx->flag, c);
+  ECSEG_CHECK_LAUNCH();
+  return ECSEG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// size_thresh  (image_tools.py:41-59), all three rules from one labelling snapshot
+// ------------------------------------------------------------------------------------------------
+__global__ void k_size_apply(uint8_t* __restrict__ cls, int h, int w, const int32_t* __restrict__ L,
+                             const int32_t* __restrict__ area, const Counters* __restrict__ cnt) {
+  PIXEL_XY();
+  if (x >= w) return;
+  const int i = y * w + x;
+  const int r = L[i];
+  if (r < 0) return;
+  const int v = cls[i];
+  const long long a = area[r];
+  // `area < np.mean(areas)`  <=>  area * count < sum(areas); an empty list gives NaN -> False.
+  if (v == 1) {
+    const long long n2 = cnt->ncomp[2];
+    if (n2 > 0 && a * n2 < (long long)cnt->npix[2]) cls[i] = 0;
+  } else if (v == 2) {
+    const long long n3 = cnt->ncomp[3];
+    if (n3 > 0 && a * n3 < (long long)cnt->npix[3]) cls[i] = 3;
+  } else if (v == 3) {
+    if (a < kEcSizeThreshold) cls[i] = 0;
+  }
+}
+
+int pp_size_thresh(ecseg_ctx* ctx, uint8_t* cls, int h, int w, cudaStream_t st) {
+  ECSEG_TRY(ccl_run(ctx, cls, h, w, KEY_CLASS, 0, /*conn8=*/1, st));
+  k_ccl_accumulate<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, ctx->L, ctx->area, ctx->sum_y, ctx->sum_x, 0,
+                                                         ctx->counters);
+  ECSEG_CHECK_LAUNCH();
+  k_size_apply<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, ctx->L, ctx->area, ctx->counters);
+  ECSEG_CHECK_LAUNCH();
+  return ECSEG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3-cross morphology on the ecDNA mask
+// ------------------------------------------------------------------------------------------------
+// image_tools.py:64: img[dilate(ec) XOR erode(ec)] = 0; erosion treats outside-image as ecDNA.
+__global__ void k_ec_boundary_erase(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int h, int w) {
+  PIXEL_XY();
+  if (x >= w) return;
+  const int i = y * w + x;
+  const uint8_t v = src[i];
+  const bool c = v == 3;
+  const bool up = y > 0 ? src[i - w] == 3 : false, dn = y < h - 1 ? src[i + w] == 3 : false;
+  const bool lf = x > 0 ? src[i - 1] == 3 : false, rt = x < w - 1 ? src[i + 1] == 3 : false;
+  const bool dil = c || up || dn || lf || rt;
+  const bool ero = c && (y > 0 ? up : true) && (y < h - 1 ? dn : true) && (x > 0 ? lf : true) && (x < w - 1 ? rt : true);
+  dst[i] = (dil != ero) ? 0 : v;
+}
+
+// image_tools.py:83: img[dilate(img == 3)] = 3
+__global__ void k_ec_dilate(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int h, int w) {
+  PIXEL_XY();
+  if (x >= w) return;
+  const int i = y * w + x;
+  const uint8_t v = src[i];
+  const bool d = v == 3 || (y > 0 && src[i - w] == 3) || (y < h - 1 && src[i + w] == 3) ||
+                 (x > 0 && src[i - 1] == 3) || (x < w - 1 && src[i + 1] == 3);
+  dst[i] = d ? 3 : v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// nucleus-in-metaphase removal  (image_tools.py:66-81)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_compact_centroids(const uint8_t* __restrict__ cls, int h, int w, const int32_t* __restrict__ L,
+                                    const int32_t* __restrict__ area, const unsigned long long* __restrict__ sy,
+                                    const unsigned long long* __restrict__ sx, double* __restrict__ ccy,
+                                    double* __restrict__ ccx, int32_t* __restrict__ nuc, Counters* __restrict__ cnt) {
+  PIXEL_XY();
+  if (x >= w) return;
+  const int i = y * w + x;
+  if (L[i] != i) return;
+  const int v = cls[i];
+  if (v == 2) {
+    const int j = atomicAdd(&cnt->n_chrom, 1);
+    const double n = (double)area[i];
+    ccy[j] = __ddiv_rn((double)sy[i], n);
+    ccx[j] = __ddiv_rn((double)sx[i], n);
+  } else if (v == 1) {
+    nuc[atomicAdd(&cnt->n_nuc, 1)] = i;
+  }
+}
+
+// One block per nucleus component: count chromosome centroids in the four open half-windows.
+__global__ void k_nucleus_decide(const int32_t* __restrict__ nuc, const double* __restrict__ ccy,
+                                 const double* __restrict__ ccx, const int32_t* __restrict__ area,
+                                 const unsigned long long* __restrict__ sy, const unsigned long long* __restrict__ sx,
+                                 int32_t* __restrict__ flag, const Counters* __restrict__ cnt) {
+  __shared__ int s[4];
+  const int n_nuc = cnt->n_nuc, n_chrom = cnt->n_chrom;
+  for (int j = blockIdx.x; j < n_nuc; j += gridDim.x) {
+    if (threadIdx.x < 4) s[threadIdx.x] = 0;
+    __syncthreads();
+    const int root = nuc[j];
+    const double a = (double)area[root];
+    const double ny = __ddiv_rn((double)sy[root], a), nx = __ddiv_rn((double)sx[root], a);
+    const double nx_hi = __dadd_rn(nx, kChromWindow), nx_lo = __dsub_rn(nx, kChromWindow);
+    const double ny_hi = __dadd_rn(ny, kChromWindow), ny_lo = __dsub_rn(ny, kChromWindow);
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    for (int t = threadIdx.x; t < n_chrom; t += blockDim.x) {
+      const double cy = ccy[t], cx = ccx[t];
+      c0 += (cx > nx) && (cx < nx_hi);   // "left"   (image_tools.py:76)
+      c1 += (cx < nx) && (cx > nx_lo);   // "right"  (:77)
+      c2 += (cy < ny) && (cy > ny_lo);   // "bottom" (:78)
+      c3 += (cy > ny) && (cy < ny_hi);   // "top"    (:79)
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      c0 += __shfl_xor_sync(0xffffffffu, c0, o); c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+      c2 += __shfl_xor_sync(0xffffffffu, c2, o); c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s[0], c0); atomicAdd(&s[1], c1); atomicAdd(&s[2], c2); atomicAdd(&s[3], c3); }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      flag[root] = (s[0] > kMinChromCount && s[1] > kMinChromCount && s[2] > kMinChromCount && s[3] > kMinChromCount);
+    __syncthreads();
+  }
+}
+
+__global__ void k_nucleus_apply(uint8_t* __restrict__ cls, int h, int w, const int32_t* __restrict__ L,
+                                const int32_t* __restrict__ flag) {
+  PIXEL_XY();
+  if (x >= w) return;
+  const int i = y * w + x;
+  if (cls[i] == 1 && flag[L[i]]) cls[i] = 0;
+}
+
+static int pp_nucleus_in_metaphase(ecseg_ctx* ctx, uint8_t* cls, int h, int w, cudaStream_t st) {
+  ECSEG_TRY(ccl_run(ctx, cls, h, w, KEY_CLASS, 0, /*conn8=*/1, st));
+  k_ccl_accumulate<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, ctx->L, ctx->area, ctx->sum_y, ctx->sum_x, 1,
+                                                         ctx->counters);
+  ECSEG_CHECK_LAUNCH();
+  k_compact_centroids<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, ctx->L, ctx->area, ctx->sum_y, ctx->sum_x,
+                                                            ctx->chrom_cy, ctx->chrom_cx, ctx->nuc_roots, ctx->counters);
+  ECSEG_CHECK_LAUNCH();
+  k_nucleus_decide<<<296, 256, 0, st>>>(ctx->nuc_roots, ctx->chrom_cy, ctx->chrom_cx, ctx->area, ctx->sum_y,
+                                        ctx->sum_x, ctx->flag, ctx->counters);
+  ECSEG_CHECK_LAUNCH();
+  k_nucleus_apply<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, ctx->L, ctx->flag);
+  ECSEG_CHECK_LAUNCH();
+  return ECSEG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// merge_comp  (image_tools.py:18-33)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_mark_has_class(const uint8_t* __restrict__ cls, int h, int w, const int32_t* __restrict__ L,
+                                 int32_t* __restrict__ flag, int c) {
+  PIXEL_XY();
+  if (x >= w) return;
+  const int i = y * w + x;
+  if (cls[i] == c) flag[L[i]] = 1;
+}
+
+// Components (of everything but the masked class) that contain class c become all-c, except the
+// raster-last component: `for i in range(1, num_features)` never visits label == num_features.
+__global__ void k_merge_convert(uint8_t* __restrict__ cls, int h, int w, const int32_t* __restrict__ L,
+                                const int32_t* __restrict__ flag, int c, const Counters* __restrict__ cnt) {
+  PIXEL_XY();
+  if (x >= w) return;
+  const int i = y * w + x;
+  const int r = L[i];
+  if (r >= 0 && r != cnt->last_root && flag[r]) cls[i] = (uint8_t)c;
+}
+
+// grey erosion with the cross; scipy mode 'reflect' == out-of-image neighbours repeat the edge
+// pixel, i.e. they never lower the minimum.  The masked class reads as 0 (image_tools.py:22-23).
+__global__ void k_grey_erode_masked(const uint8_t* __restrict__ cls, uint8_t* __restrict__ dst, int h, int w, int mask_id) {
+  PIXEL_XY();
+  if (x >= w) return;
+  const int i = y * w + x;
+  auto val = [&](int j) -> int { int v = cls[j]; return v == mask_id ? 0 : v; };
+  int m = val(i);
+  if (y > 0) m = min(m, val(i - w));
+  if (y < h - 1) m = min(m, val(i + w));
+  if (x > 0) m = min(m, val(i - 1));
+  if (x < w - 1) m = min(m, val(i + 1));
+  dst[i] = (uint8_t)m;
+}
+
+// grey dilation of the eroded image; where the opening equals c the pixel becomes c, then the
+// masked class is restored (image_tools.py:31-32) -- i.e. masked pixels are left untouched.
+__global__ void k_open_apply(uint8_t* __restrict__ cls, const uint8_t* __restrict__ ero, int h, int w, int c, int mask_id) {
+  PIXEL_XY();
+  if (x >= w) return;
+  const int i = y * w + x;
+  int m = ero[i];
+  if (y > 0) m = max(m, (int)ero[i - w]);
+  if (y < h - 1) m = max(m, (int)ero[i + w]);
+  if (x > 0) m = max(m, (int)ero[i - 1]);
+  if (x < w - 1) m = max(m, (int)ero[i + 1]);
+  if (m == c && cls[i] != mask_id) cls[i] = (uint8_t)c;
+}
+
+int pp_merge_comp(ecseg_ctx* ctx, uint8_t* cls, int h, int w, int c, cudaStream_t st) {
+  if (c != 1 && c != 2) { ctx->err = "merge_comp: class_id must be 1 or 2"; return ECSEG_E_INVALID; }
+  const int mask_id = (c == 1) ? 2 : 1;
+  ECSEG_TRY(ccl_run(ctx, cls, h, w, KEY_NZ_EXCEPT, mask_id, /*conn8=*/1, st));
+  k_mark_has_class<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, ctx->L, ctx->flag, c);
+  ECSEG_CHECK_LAUNCH();
+  k_merge_convert<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, ctx->L, ctx->flag, c, ctx->counters);
+  ECSEG_CHECK_LAUNCH();
+  k_grey_erode_masked<<<px_grid(h, w), px_block(), 0, st>>>(cls, ctx->tmp_b, h, w, mask_id);
+  ECSEG_CHECK_LAUNCH();
+  k_open_apply<<<px_grid(h, w), px_block(), 0, st>>>(cls, ctx->tmp_b, h, w, c, mask_id);
+  ECSEG_CHECK_LAUNCH();
+  return ECSEG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// count_cc  (image_tools.py:114-119)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_count_finish(const Counters* __restrict__ cnt, long long n_px, int32_t* d_n, int64_t* d_px) {
+  if (threadIdx.x || blockIdx.x) return;
+  const int n = cnt->ncomp[1];
+  long long px = (long long)cnt->npix[0];
+  // np.unique(labels)[1:] drops the smallest label on the assumption that it is background; with no
+  // background pixel at all the single component itself is dropped.
+  if (n > 0 && px == n_px) px = 0;
+  if (d_n) *d_n = n;
+  if (d_px) *d_px = px;
+}
+
+static int count_mode(ecseg_ctx* ctx, const uint8_t* cls, int h, int w, int mode, int c, int32_t* d_n, int64_t* d_px,
+                      cudaStream_t st) {
+  ECSEG_TRY(ccl_run(ctx, cls, h, w, mode, c, /*conn8=*/1, st));
+  k_count_finish<<<1, 32, 0, st>>>(ctx->counters, (long long)h * w, d_n, d_px);
+  ECSEG_CHECK_LAUNCH();
+  return ECSEG_OK;
+}
+
+int pp_count_cc(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w, int32_t* d_n, int64_t* d_px, cudaStream_t st) {
+  return count_mode(ctx, d_mask, h, w, KEY_NONZERO, 0, d_n, d_px, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic labelling for tests:  0 background, else 1 + root index
+// ------------------------------------------------------------------------------------------------
+__global__ void k_label_export(const int32_t* __restrict__ L, int n, int32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = L[i] + 1;
+}
+
+int pp_label(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w, int conn, int32_t* d_out, cudaStream_t st) {
+  if (conn != 4 && conn != 8) { ctx->err = "label: connectivity must be 4 or 8"; return ECSEG_E_INVALID; }
+  ECSEG_TRY(ccl_run(ctx, d_mask, h, w, KEY_CLASS, 0, conn == 8, st));
+  k_label_export<<<cdiv((long long)h * w, 256), 256, 0, st>>>(ctx->L, h * w, d_out);
+  ECSEG_CHECK_LAUNCH();
+  return ECSEG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// meta_inference in execution order  (image_tools.py:61-83)  + count_cc(I == 3)
+// ------------------------------------------------------------------------------------------------
+int pp_postprocess(ecseg_ctx* ctx, uint8_t* cls, int h, int w, int flags, int32_t* d_n_ec, int64_t* d_ec_px,
+                   cudaStream_t st) {
+  if (!cls || h < 1 || w < 1 || (size_t)h * w > ctx->max_px) {
+    ctx->err = "ecseg_postprocess: image larger than the context's max_h x max_w";
+    return ECSEG_E_INVALID;
+  }
+  uint8_t* t = ctx->tmp_a;
+  ECSEG_TRY(pp_fill_holes(ctx, cls, h, w, 1, st));                       // :61
+  ECSEG_TRY(pp_fill_holes(ctx, cls, h, w, 2, st));                       // :61
+  ECSEG_TRY(pp_size_thresh(ctx, cls, h, w, st));                         // :62
+  k_ec_boundary_erase<<<px_grid(h, w), px_block(), 0, st>>>(cls, t, h, w);  // :64   cls -> t
+  ECSEG_CHECK_LAUNCH();
+  ECSEG_TRY(pp_nucleus_in_metaphase(ctx, t, h, w, st));                  // :66-81
+  if (flags & ECSEG_PP_FAITHFUL_MERGE) {                                 // :82 (no-op here)
+    ECSEG_TRY(pp_merge_comp(ctx, t, h, w, 1, st));
+    ECSEG_TRY(pp_merge_comp(ctx, t, h, w, 2, st));
+  }
+  k_ec_dilate<<<px_grid(h, w), px_block(), 0, st>>>(t, cls, h, w);       // :83   t -> cls
+  ECSEG_CHECK_LAUNCH();
+  if (d_n_ec || d_ec_px) ECSEG_TRY(count_mode(ctx, cls, h, w, KEY_EQ, 3, d_n_ec, d_ec_px, st));  // metaseg.py:46
+  return ECSEG_OK;
+}
+
+}  // namespace ecseg

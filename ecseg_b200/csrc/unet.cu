@@ -1,0 +1,554 @@
+// metaseg U-Net forward: weight folding/packing, activation workspace, layer schedule.
+//
+// Replaces model.predict_on_batch (reference call site src/utils.py:115).  Architecture: the
+// topology template src/model_layers/models.py:17-136 with 1 input channel, 4 classes, softmax
+// (ecseg_b200/spec.py holds the same table).
+//
+// Two arithmetic modes share the schedule:
+//   * fp32  : CUDA-core FMA direct convolution (k_conv_fp32) -- parity mode.
+//   * bf16 / fp16 : tcgen05 implicit GEMM (conv_tc.cu) -- throughput mode.
+// Activations are NHWC; skip connections are written straight into the first half of the concat
+// buffer and the transposed convolutions into the second half, so no concat kernel exists.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "conv_tc.cuh"
+#include "stitch.cuh"
+
+namespace ecseg {
+
+namespace {
+
+constexpr double kBnEps = 1e-3;  // Keras BatchNormalization default
+
+struct LayerDef {
+  const char* name;
+  int convT, cin, cout, relu, bias, level;
+};
+// must match ecseg_b200/spec.py UNET_LAYERS
+const LayerDef kLayers[23] = {
+    {"conv1-1", 0, 1, 64, 1, 1, 0},     {"conv1-2", 0, 64, 64, 1, 1, 0},    {"conv2-1", 0, 64, 128, 1, 1, 1},
+    {"conv2-2", 0, 128, 128, 1, 1, 1},  {"conv3-1", 0, 128, 256, 1, 1, 2},  {"conv3-2", 0, 256, 256, 1, 1, 2},
+    {"conv4-1", 0, 256, 512, 1, 1, 3},  {"conv4-2", 0, 512, 512, 1, 1, 3},  {"conv5-1", 0, 512, 1024, 1, 1, 4},
+    {"conv5-2", 0, 1024, 1024, 1, 1, 4}, {"up4", 1, 1024, 512, 1, 1, 3},    {"conv4-3", 0, 512, 512, 1, 1, 3},
+    {"conv4-4", 0, 512, 512, 1, 1, 3},  {"up3", 1, 512, 256, 0, 1, 2},      {"conv3-3", 0, 512, 256, 1, 1, 2},
+    {"conv3-4", 0, 256, 256, 1, 1, 2},  {"up2", 1, 256, 128, 0, 1, 1},      {"conv2-3", 0, 256, 128, 1, 1, 1},
+    {"conv2-4", 0, 128, 128, 1, 1, 1},  {"up1", 1, 128, 64, 0, 1, 0},       {"conv1-3", 0, 128, 64, 1, 1, 0},
+    {"conv1-4", 0, 64, 64, 1, 1, 0},    {"final", 0, 64, 4, 0, 0, 0}};
+
+enum Buf { A0, B0, CAT1, P1, A1, B1, CAT2, P2, A2, B2, CAT3, P3, A3, B3, P4, A4, B4, kNumBufs };
+struct BufDef { int level, ch; };
+const BufDef kBufs[kNumBufs] = {{0, 64}, {0, 64}, {0, 128}, {1, 64},  {1, 128}, {1, 128}, {1, 256}, {2, 128}, {2, 256},
+                                {2, 256}, {2, 512}, {3, 256}, {3, 512}, {3, 512}, {4, 512}, {4, 1024}, {4, 1024}};
+
+// layer -> (input buffer, output buffer, output channel offset, pool-after destination or -1)
+struct Wire { int in, out, choff, pool_to; };
+const Wire kWires[23] = {
+    {-1, A0, 0, -1},   {A0, CAT1, 0, P1},  {P1, A1, 0, -1},    {A1, CAT2, 0, P2},   {P2, A2, 0, -1},   {A2, CAT3, 0, P3},
+    {P3, A3, 0, -1},   {A3, B3, 0, P4},    {P4, A4, 0, -1},    {A4, B4, 0, -1},     {B4, A3, 0, -1},   {A3, B3, 0, -1},
+    {B3, A3, 0, -1},   {A3, CAT3, 256, -1}, {CAT3, A2, 0, -1}, {A2, B2, 0, -1},     {B2, CAT2, 128, -1}, {CAT2, A1, 0, -1},
+    {A1, B1, 0, -1},   {B1, CAT1, 64, -1}, {CAT1, A0, 0, -1},  {A0, B0, 0, -1},     {B0, -1, 0, -1}};
+
+}  // namespace
+
+struct UNet {
+  int precision = -1;
+  int esize = 0;  // bytes per activation element
+  void* buf[kNumBufs] = {};
+  // per layer device weights
+  void* w[23] = {};      // tc: 16-bit [tap][cout_rows][cin]; fp32: float [tap][cin][cout_pad]; layer 0: float [9][64]
+  float* b[23] = {};     // folded bias [cout] (nullptr for the head)
+  int cout_rows[23] = {};
+  float* debug_dump = nullptr;
+  // tcgen05 knobs (ECSEG_TC_PITCH / ECSEG_TC_DESC_MODE / ECSEG_TC_NTILE_MAX env overrides)
+  int tc_pitch = 18, tc_desc_mode = 0, tc_ntile_max = 256;
+  int stop_after = -1;   // debug: stop the forward after this layer
+};
+
+// ------------------------------------------------------------------------------------------------
+// element helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// ------------------------------------------------------------------------------------------------
+// conv1-1: Cin = 1, K = 9 -> CUDA cores.  Reads raw uint8 0..255 (reference feeds the tiles
+// un-normalised, src/utils.py:113-115) either from materialised tiles or straight from the
+// pre-processed image through the tile grid (fused im2patches_overlap).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_conv_first(const uint8_t* __restrict__ tiles, const uint8_t* __restrict__ pre,
+                                                    TileGrid g, const float* __restrict__ w9x64,
+                                                    const float* __restrict__ bias, T* __restrict__ out) {
+  __shared__ float sw[9 * 64];
+  __shared__ float sb[64];
+  for (int i = threadIdx.x; i < 9 * 64; i += 256) sw[i] = w9x64[i];
+  if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int img = blockIdx.z, y = blockIdx.y;
+  const int x = blockIdx.x * 32 + (threadIdx.x >> 3);
+  const int cg = (threadIdx.x & 7) * 8;
+  const uint8_t* src;
+  int pitch;
+  if (tiles) { src = tiles + (size_t)img * kTile * kTile; pitch = kTile; }
+  else {
+    const int ri = img % g.nr, ci = img / g.nr;
+    src = pre + (size_t)g.start_r(ri) * g.w + g.start_c(ci);
+    pitch = g.w;
+  }
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = sb[cg + j];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = y + ky - 1;
+    if (yy < 0 || yy >= kTile) continue;   // 'same' padding at the TILE border (tile-wise semantics)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = x + kx - 1;
+      if (xx < 0 || xx >= kTile) continue;
+      const float v = (float)src[(size_t)yy * pitch + xx];
+      const float* wp = sw + (ky * 3 + kx) * 64 + cg;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wp[j], acc[j]);
+    }
+  }
+  T* dst = out + (((size_t)img * kTile + y) * kTile + x) * 64 + cg;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dst[j] = from_f<T>(fmaxf(acc[j], 0.f));
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2x2 max pool, NHWC, source may be the leading C channels of a wider (concat) buffer
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_maxpool(const T* __restrict__ in, int in_pitch, int C, int Ho, int Wo, T* __restrict__ out, size_t total) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  size_t pix = i / C;
+  const int x = (int)(pix % Wo); pix /= Wo;
+  const int y = (int)(pix % Ho);
+  const size_t n = pix / Ho;
+  const T* p = in + ((n * (2 * Ho) + 2 * y) * (size_t)(2 * Wo) + 2 * x) * in_pitch + c;
+  const float a = to_f(p[0]), b = to_f(p[in_pitch]);
+  const float d = to_f(p[(size_t)2 * Wo * in_pitch]), e = to_f(p[(size_t)2 * Wo * in_pitch + in_pitch]);
+  out[i] = from_f<T>(fmaxf(fmaxf(a, b), fmaxf(d, e)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 parity convolution (CUDA cores).  Block = 8x8 pixels x 64 output channels, 256 threads,
+// each thread 4 pixels x 4 channels; K loop = 16-channel chunks, the 10x10 halo and the 9 tap
+// weight tiles of a chunk are staged in shared memory.  Handles conv, transposed conv (tap lists
+// per output parity) and the softmax head through the same tap description as the tensor-core
+// kernel.
+// ------------------------------------------------------------------------------------------------
+struct ConvF32Params {
+  const float* in; int in_pitch, cin;
+  int H, W;                // input grid
+  const float* w;          // [tap 9][cin][cout_pad]
+  int cout_pad;
+  const float* bias; int relu;
+  int n_par;
+  int n_taps[kMaxPar];
+  signed char tap_dy[kMaxPar][kMaxTaps], tap_dx[kMaxPar][kMaxTaps], tap_w[kMaxPar][kMaxTaps];
+  signed char par_oy[kMaxPar], par_ox[kMaxPar];
+  int oscale;
+  float* out; int out_H, out_W, out_pitch, out_choff;
+  int head;
+  float* probs; float* logits; uint8_t* labels; TileGrid grid;
+};
+
+__global__ void __launch_bounds__(256) k_conv_fp32(const ConvF32Params p) {
+  __shared__ float s_in[16][104];       // [channel][10x10 halo (+pad)]
+  __shared__ float s_w[9][16][64];      // [tap][channel][cout]
+  const int tid = threadIdx.x;
+  const int bw = p.W >> 3;
+  const int bx = blockIdx.x % bw, by = blockIdx.x / bw;
+  const int img = blockIdx.z / p.n_par, par = blockIdx.z % p.n_par;
+  const int co0 = blockIdx.y * 64;
+  const int y0 = by * 8, x0 = bx * 8;
+  const int pg = tid >> 4, cg = (tid & 15) * 4;
+  const int ntaps = p.n_taps[par];
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int c0 = 0; c0 < p.cin; c0 += 16) {
+    __syncthreads();
+    for (int e = tid; e < 100 * 16; e += 256) {
+      const int ci = e & 15, hp = e >> 4;
+      const int hy = hp / 10, hx = hp % 10;
+      const int yy = y0 + hy - 1, xx = x0 + hx - 1;
+      float v = 0.f;
+      if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
+        v = p.in[(((size_t)img * p.H + yy) * p.W + xx) * p.in_pitch + c0 + ci];
+      s_in[ci][hp] = v;
+    }
+    for (int e = tid; e < ntaps * 16 * 64; e += 256) {
+      const int co = e & 63, ci = (e >> 6) & 15, t = e >> 10;
+      s_w[t][ci][co] = p.w[((size_t)p.tap_w[par][t] * p.cin + c0 + ci) * p.cout_pad + co0 + co];
+    }
+    __syncthreads();
+    for (int t = 0; t < ntaps; ++t) {
+      const int dy = p.tap_dy[par][t], dx = p.tap_dx[par][t];
+#pragma unroll 4
+      for (int ci = 0; ci < 16; ++ci) {
+        const float4 wv = *reinterpret_cast<const float4*>(&s_w[t][ci][cg]);
+        float a[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int pi = pg * 4 + i;
+          a[i] = s_in[ci][((pi >> 3) + dy) * 10 + (pi & 7) + dx];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[i][0] = fmaf(a[i], wv.x, acc[i][0]); acc[i][1] = fmaf(a[i], wv.y, acc[i][1]);
+          acc[i][2] = fmaf(a[i], wv.z, acc[i][2]); acc[i][3] = fmaf(a[i], wv.w, acc[i][3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pi = pg * 4 + i;
+    const int y = y0 + (pi >> 3), x = x0 + (pi & 7);
+    if (p.head) {
+      if (cg != 0 || co0 != 0) continue;
+      float z[4] = {acc[i][0], acc[i][1], acc[i][2], acc[i][3]}, pr[4];
+      softmax4(z, pr);
+      const size_t pix = ((size_t)img * kTile + y) * kTile + x;
+      if (p.logits) reinterpret_cast<float4*>(p.logits)[pix] = make_float4(z[0], z[1], z[2], z[3]);
+      if (p.probs) reinterpret_cast<float4*>(p.probs)[pix] = make_float4(pr[0], pr[1], pr[2], pr[3]);
+      if (p.labels) {
+        int err = 0;
+        stitch_write_owned(p.grid, img, y, x, quantised_argmax(pr[0], pr[1], pr[2], pr[3], &err), p.labels);
+      }
+    } else {
+      const int oy = y * p.oscale + p.par_oy[par], ox = x * p.oscale + p.par_ox[par];
+      float4 o;
+      float* f = reinterpret_cast<float*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = acc[i][j] + (p.bias ? p.bias[co0 + cg + j] : 0.f);
+        f[j] = p.relu ? fmaxf(v, 0.f) : v;
+      }
+      *reinterpret_cast<float4*>(p.out + (((size_t)img * p.out_H + oy) * p.out_W + ox) * p.out_pitch + p.out_choff +
+                                 co0 + cg) = o;
+    }
+  }
+}
+
+// 16-bit / fp32 activation -> fp32 dense copy for ecseg_debug_layer_output
+template <typename T>
+__global__ void k_export_layer(const T* __restrict__ in, int pitch, int choff, int C, size_t npix, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * C) return;
+  const size_t pix = i / C;
+  const int c = (int)(i % C);
+  out[i] = to_f(in[pix * pitch + choff + c]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tap tables shared by both conv paths
+// ------------------------------------------------------------------------------------------------
+template <typename P>
+static void fill_taps(P& p, bool convT) {
+  if (!convT) {
+    p.n_par = 1; p.oscale = 1; p.par_oy[0] = p.par_ox[0] = 0;
+    p.n_taps[0] = 9;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        const int t = ky * 3 + kx;
+        p.tap_dy[0][t] = (signed char)ky; p.tap_dx[0][t] = (signed char)kx; p.tap_w[0][t] = (signed char)t;
+      }
+    return;
+  }
+  // TF 'same' stride-2 transposed conv: out[2i+ky, 2j+kx] += in[i,j] * K[ky,kx], cropped to 2H x 2W.
+  // Output parity (py,px): ky in {0,2} for py == 0 (input rows i and i-1), ky == 1 for py == 1.
+  p.n_par = 4; p.oscale = 2;
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      const int par = py * 2 + px;
+      p.par_oy[par] = (signed char)py; p.par_ox[par] = (signed char)px;
+      int n = 0;
+      for (int ky = py; ky < 3; ky += 2)
+        for (int kx = px; kx < 3; kx += 2) {
+          p.tap_dy[par][n] = (signed char)(ky == 2 ? 0 : 1);   // halo row of input (i-1) is 0, of i is 1
+          p.tap_dx[par][n] = (signed char)(kx == 2 ? 0 : 1);
+          p.tap_w[par][n] = (signed char)(ky * 3 + kx);
+          ++n;
+        }
+      p.n_taps[par] = n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------------
+int unet_create(ecseg_ctx* ctx) {
+  ctx->net = new UNet();
+  if (const char* e = getenv("ECSEG_TC_PITCH")) ctx->net->tc_pitch = atoi(e);
+  if (const char* e = getenv("ECSEG_TC_DESC_MODE")) ctx->net->tc_desc_mode = atoi(e);
+  if (const char* e = getenv("ECSEG_TC_NTILE_MAX")) ctx->net->tc_ntile_max = atoi(e);
+  return ECSEG_OK;
+}
+
+static void free_net_buffers(UNet* n) {
+  for (auto& b : n->buf) { if (b) cudaFree(b); b = nullptr; }
+  for (int l = 0; l < 23; ++l) {
+    if (n->w[l]) cudaFree(n->w[l]);
+    if (n->b[l]) cudaFree(n->b[l]);
+    n->w[l] = nullptr; n->b[l] = nullptr;
+  }
+  if (n->debug_dump) { cudaFree(n->debug_dump); n->debug_dump = nullptr; }
+}
+
+void unet_destroy(ecseg_ctx* ctx) {
+  if (!ctx->net) return;
+  free_net_buffers(ctx->net);
+  delete ctx->net;
+  ctx->net = nullptr;
+}
+
+static uint16_t f2h_bits(float f, bool bf16) {
+  if (bf16) { __nv_bfloat16 h = __float2bfloat16_rn(f); uint16_t u; memcpy(&u, &h, 2); return u; }
+  __half h = __float2half_rn(f); uint16_t u; memcpy(&u, &h, 2); return u;
+}
+
+int unet_load_weights(ecseg_ctx* ctx, const float* blob, size_t n_floats, int precision) {
+  UNet* net = ctx->net;
+  if (!net || ctx->max_tiles <= 0) { ctx->err = "load_weights: context was created with max_tiles == 0"; return ECSEG_E_STATE; }
+  if (precision < 0 || precision > 2) { ctx->err = "load_weights: precision must be 0 (fp32), 1 (bf16) or 2 (fp16)"; return ECSEG_E_INVALID; }
+  size_t need = 0;
+  for (const auto& l : kLayers) need += (size_t)9 * l.cin * l.cout + 5 * (size_t)l.cout + 1;
+  if (n_floats != need) {
+    ctx->err = "load_weights: blob has " + std::to_string(n_floats) + " floats, expected " + std::to_string(need);
+    return ECSEG_E_INVALID;
+  }
+  free_net_buffers(net);
+  net->precision = precision;
+  net->esize = precision == ECSEG_PREC_FP32 ? 4 : 2;
+  const bool tc = precision != ECSEG_PREC_FP32, bf16 = precision == ECSEG_PREC_BF16;
+
+  // activation workspace
+  for (int i = 0; i < kNumBufs; ++i) {
+    const size_t hw = (size_t)(kTile >> kBufs[i].level) * (kTile >> kBufs[i].level);
+    ECSEG_CUDA(cudaMalloc(&net->buf[i], (size_t)ctx->max_tiles * hw * kBufs[i].ch * net->esize));
+  }
+  ECSEG_CUDA(cudaMalloc(&net->debug_dump, 2 * 128 * 256 * sizeof(float)));
+
+  // fold BatchNorm and repack
+  const float* q = blob;
+  for (int li = 0; li < 23; ++li) {
+    const LayerDef& l = kLayers[li];
+    const float* K = q; q += (size_t)9 * l.cin * l.cout;
+    const float* bias = q; q += l.cout;
+    const bool bn = *q++ != 0.f;
+    const float *gamma = q, *beta = q + l.cout, *mean = q + 2 * l.cout, *var = q + 3 * l.cout;
+    q += 4 * (size_t)l.cout;
+    std::vector<double> scale(l.cout, 1.0);
+    std::vector<float> fb(l.cout);
+    for (int co = 0; co < l.cout; ++co) {
+      double b = l.bias ? (double)bias[co] : 0.0;
+      if (bn) {
+        scale[co] = (double)gamma[co] / std::sqrt((double)var[co] + kBnEps);
+        b = (b - (double)mean[co]) * scale[co] + (double)beta[co];
+      }
+      fb[co] = (float)b;
+    }
+    auto kval = [&](int tap, int ci, int co) -> float {   // folded weight, Keras layouts
+      const size_t idx = l.convT ? (((size_t)tap * l.cout + co) * l.cin + ci) : (((size_t)tap * l.cin + ci) * l.cout + co);
+      return (float)((double)K[idx] * scale[co]);
+    };
+    if (l.bias || bn) {
+      ECSEG_CUDA(cudaMalloc(&net->b[li], l.cout * sizeof(float)));
+      ECSEG_CUDA(cudaMemcpy(net->b[li], fb.data(), l.cout * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (li == 0) {   // [9][64] fp32 for the CUDA-core first layer
+      std::vector<float> w(9 * 64);
+      for (int t = 0; t < 9; ++t) for (int co = 0; co < 64; ++co) w[t * 64 + co] = kval(t, 0, co);
+      ECSEG_CUDA(cudaMalloc(&net->w[li], w.size() * sizeof(float)));
+      ECSEG_CUDA(cudaMemcpy(net->w[li], w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+      net->cout_rows[li] = 64;
+    } else if (tc) {   // [tap][cout_rows][cin] 16-bit, K-major rows for TMA / UMMA
+      const int rows = l.cout < 16 ? 16 : l.cout;
+      std::vector<uint16_t> w((size_t)9 * rows * l.cin, 0);
+      for (int t = 0; t < 9; ++t)
+        for (int co = 0; co < l.cout; ++co)
+          for (int ci = 0; ci < l.cin; ++ci) w[((size_t)t * rows + co) * l.cin + ci] = f2h_bits(kval(t, ci, co), bf16);
+      ECSEG_CUDA(cudaMalloc(&net->w[li], w.size() * 2));
+      ECSEG_CUDA(cudaMemcpy(net->w[li], w.data(), w.size() * 2, cudaMemcpyHostToDevice));
+      net->cout_rows[li] = rows;
+    } else {           // [tap][cin][cout_pad] fp32
+      const int pad = (l.cout + 63) / 64 * 64;
+      std::vector<float> w((size_t)9 * l.cin * pad, 0.f);
+      for (int t = 0; t < 9; ++t)
+        for (int ci = 0; ci < l.cin; ++ci)
+          for (int co = 0; co < l.cout; ++co) w[((size_t)t * l.cin + ci) * pad + co] = kval(t, ci, co);
+      ECSEG_CUDA(cudaMalloc(&net->w[li], w.size() * sizeof(float)));
+      ECSEG_CUDA(cudaMemcpy(net->w[li], w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+      net->cout_rows[li] = pad;
+    }
+  }
+  return ECSEG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int run_first(ecseg_ctx* ctx, const uint8_t* d_tiles, const uint8_t* d_pre, const TileGrid* grid, int n,
+                     cudaStream_t st) {
+  UNet* net = ctx->net;
+  TileGrid g = grid ? *grid : TileGrid{};
+  k_conv_first<T><<<dim3(kTile / 32, kTile, n), 256, 0, st>>>(d_tiles, d_pre, g, (const float*)net->w[0], net->b[0],
+                                                            (T*)net->buf[A0]);
+  ECSEG_CHECK_LAUNCH();
+  return ECSEG_OK;
+}
+
+template <typename T>
+static int run_pool(ecseg_ctx* ctx, int src, int dst, int n, cudaStream_t st) {
+  UNet* net = ctx->net;
+  const int C = kBufs[dst].ch, Ho = kTile >> kBufs[dst].level;
+  const size_t total = (size_t)n * Ho * Ho * C;
+  k_maxpool<T><<<cdiv((long long)total, 256), 256, 0, st>>>((const T*)net->buf[src], kBufs[src].ch, C, Ho, Ho,
+                                                           (T*)net->buf[dst], total);
+  ECSEG_CHECK_LAUNCH();
+  return ECSEG_OK;
+}
+
+static int run_layer_fp32(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_logits, uint8_t* d_labels,
+                          const TileGrid* grid, cudaStream_t st) {
+  UNet* net = ctx->net;
+  const LayerDef& l = kLayers[li];
+  const Wire& wr = kWires[li];
+  ConvF32Params p;
+  memset(&p, 0, sizeof(p));
+  fill_taps(p, l.convT != 0);
+  const int out_hw = kTile >> l.level;
+  const int in_hw = l.convT ? out_hw / 2 : out_hw;
+  p.in = (const float*)net->buf[wr.in]; p.in_pitch = kBufs[wr.in].ch; p.cin = l.cin;
+  p.H = in_hw; p.W = in_hw;
+  p.w = (const float*)net->w[li]; p.cout_pad = net->cout_rows[li];
+  p.bias = net->b[li]; p.relu = l.relu;
+  p.head = li == 22;
+  if (p.head) {
+    p.probs = d_probs; p.logits = d_logits; p.labels = d_labels;
+    if (grid) p.grid = *grid;
+  } else {
+    p.out = (float*)net->buf[wr.out]; p.out_H = out_hw; p.out_W = out_hw;
+    p.out_pitch = kBufs[wr.out].ch; p.out_choff = wr.choff;
+  }
+  dim3 gridDim((in_hw / 8) * (in_hw / 8), p.cout_pad / 64, n * p.n_par);
+  k_conv_fp32<<<gridDim, 256, 0, st>>>(p);
+  ECSEG_CHECK_LAUNCH();
+  return ECSEG_OK;
+}
+
+static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_logits, uint8_t* d_labels,
+                        const TileGrid* grid, cudaStream_t st) {
+  UNet* net = ctx->net;
+  const LayerDef& l = kLayers[li];
+  const Wire& wr = kWires[li];
+  const bool bf16 = net->precision == ECSEG_PREC_BF16;
+  ConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  fill_taps(p, l.convT != 0);
+  const int out_hw = kTile >> l.level;
+  const int in_hw = l.convT ? out_hw / 2 : out_hw;
+  const bool head = li == 22;
+  const int rows = net->cout_rows[li];
+  int n_tile = head ? 16 : (rows < net->tc_ntile_max ? rows : net->tc_ntile_max);
+  if (n_tile > 256) n_tile = 256;
+  ECSEG_TRY(make_tm_act(ctx, &p.tm_a, net->buf[wr.in], l.cin, kBufs[wr.in].ch, in_hw, in_hw, ctx->max_tiles,
+                        net->tc_pitch == 18 ? 18 : 1, bf16));
+  ECSEG_TRY(make_tm_wgt(ctx, &p.tm_b, net->w[li], l.cin, 9 * rows, n_tile, bf16));
+  p.H = in_hw; p.W = in_hw; p.n_img = n;
+  p.cin_chunks = l.cin / 64; p.n_chunks = rows / n_tile; p.cout_rows = rows;
+  p.bias = net->b[li]; p.relu = l.relu; p.is_bf16 = bf16;
+  p.desc_mode = net->tc_desc_mode;
+  p.device_error = &ctx->counters->device_error;
+  p.debug_dump = nullptr;
+  if (head) {
+    p.probs = d_probs; p.logits = d_logits; p.labels = d_labels;
+    if (grid) p.grid = *grid;
+  } else {
+    p.out = net->buf[wr.out]; p.out_H = out_hw; p.out_W = out_hw;
+    p.out_pitch = kBufs[wr.out].ch; p.out_choff = wr.choff;
+  }
+  return conv_tc_launch(ctx, p, n_tile, net->tc_pitch, head, st);
+}
+
+int unet_forward(ecseg_ctx* ctx, const uint8_t* d_tiles, const uint8_t* d_pre, const TileGrid* grid, int n,
+                 float* d_probs, float* d_logits, uint8_t* d_labels, cudaStream_t st) {
+  UNet* net = ctx->net;
+  if (!net || net->precision < 0) { ctx->err = "unet_forward: call ecseg_load_weights first"; return ECSEG_E_STATE; }
+  if (n < 1 || n > ctx->max_tiles) { ctx->err = "unet_forward: batch exceeds the context's max_tiles"; return ECSEG_E_INVALID; }
+  if (!d_tiles && !(d_pre && grid)) { ctx->err = "unet_forward: no input"; return ECSEG_E_INVALID; }
+  if (d_labels && !grid) { ctx->err = "unet_forward: fused stitch needs the tile grid"; return ECSEG_E_INVALID; }
+  const int prec = net->precision;
+  if (d_labels) ECSEG_CUDA(cudaMemsetAsync(d_labels, 0, (size_t)grid->h * grid->w, st));  // never-written strips -> 0
+  for (int li = 0; li < 23; ++li) {
+    if (li == 0) {
+      if (prec == ECSEG_PREC_FP32) ECSEG_TRY(run_first<float>(ctx, d_tiles, d_pre, grid, n, st));
+      else if (prec == ECSEG_PREC_BF16) ECSEG_TRY(run_first<__nv_bfloat16>(ctx, d_tiles, d_pre, grid, n, st));
+      else ECSEG_TRY(run_first<__half>(ctx, d_tiles, d_pre, grid, n, st));
+    } else if (prec == ECSEG_PREC_FP32) {
+      ECSEG_TRY(run_layer_fp32(ctx, li, n, d_probs, d_logits, d_labels, grid, st));
+    } else {
+      ECSEG_TRY(run_layer_tc(ctx, li, n, d_probs, d_logits, d_labels, grid, st));
+    }
+    if (net->stop_after == li) return ECSEG_OK;
+    const int pt = kWires[li].pool_to;
+    if (pt >= 0) {
+      if (prec == ECSEG_PREC_FP32) ECSEG_TRY(run_pool<float>(ctx, kWires[li].out, pt, n, st));
+      else if (prec == ECSEG_PREC_BF16) ECSEG_TRY(run_pool<__nv_bfloat16>(ctx, kWires[li].out, pt, n, st));
+      else ECSEG_TRY(run_pool<__half>(ctx, kWires[li].out, pt, n, st));
+    }
+  }
+  return ECSEG_OK;
+}
+
+int unet_debug_layer(ecseg_ctx* ctx, int layer, int n, float* d_out, cudaStream_t st) {
+  UNet* net = ctx->net;
+  if (!net || net->precision < 0 || layer < 0 || layer > 21 || n < 1 || n > ctx->max_tiles) {
+    ctx->err = "debug_layer_output: bad layer / batch or no weights";
+    return ECSEG_E_INVALID;
+  }
+  const Wire& wr = kWires[layer];
+  const int hw = kTile >> kLayers[layer].level;
+  const size_t npix = (size_t)n * hw * hw;
+  const int C = kLayers[layer].cout, pitch = kBufs[wr.out].ch;
+  const int blocks = cdiv((long long)(npix * C), 256);
+  if (net->precision == ECSEG_PREC_FP32)
+    k_export_layer<float><<<blocks, 256, 0, st>>>((const float*)net->buf[wr.out], pitch, wr.choff, C, npix, d_out);
+  else if (net->precision == ECSEG_PREC_BF16)
+    k_export_layer<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)net->buf[wr.out], pitch, wr.choff, C, npix, d_out);
+  else
+    k_export_layer<__half><<<blocks, 256, 0, st>>>((const __half*)net->buf[wr.out], pitch, wr.choff, C, npix, d_out);
+  ECSEG_CHECK_LAUNCH();
+  return ECSEG_OK;
+}
+
+int unet_set_debug(ecseg_ctx* ctx, int stop_after, int tc_pitch, int tc_desc_mode, int tc_ntile_max) {
+  UNet* net = ctx->net;
+  if (!net) return ECSEG_E_STATE;
+  net->stop_after = stop_after;
+  if (tc_pitch == 18 || tc_pitch == 24) net->tc_pitch = tc_pitch;
+  if (tc_desc_mode == 0 || tc_desc_mode == 1) net->tc_desc_mode = tc_desc_mode;
+  if (tc_ntile_max == 64 || tc_ntile_max == 128 || tc_ntile_max == 256) net->tc_ntile_max = tc_ntile_max;
+  return ECSEG_OK;
+}
+
+}  // namespace ecseg

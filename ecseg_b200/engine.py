@@ -1,0 +1,214 @@
+"""Host-side handle on one GPU's ecseg context: owns the ctypes context, moves numpy/torch buffers
+to the device and calls the C ABI.  One Engine per GPU / process (the path shards by image, no
+collective: SURVEY.md section 8e)."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_float, c_int, c_int32, c_int64, c_void_p
+
+import numpy as np
+import torch
+
+from . import _lib, spec, weights as wmod
+
+PRECISIONS = {"fp32": 0, "bf16": 1, "fp16": 2}
+PP_FAITHFUL_MERGE = 1
+
+
+def tile_grid(h: int, w: int):
+    """Tile origins of im2patches_overlap (reference src/image_tools.py:148-186) as int32 [N,2]."""
+    lib = _lib.load()
+    n, nr, nc = c_int(), c_int(), c_int()
+    rc = lib.ecseg_tile_grid(h, w, byref(n), byref(nr), byref(nc), None)
+    if rc != 0:
+        raise ValueError("images smaller than 256x256 cannot be tiled (reference limitation)")
+    pos = np.zeros((n.value, 2), np.int32)
+    lib.ecseg_tile_grid(h, w, None, None, None, pos.ctypes.data_as(c_void_p))
+    return pos, nr.value, nc.value
+
+
+class Engine:
+    def __init__(self, device: int = 0, max_h: int = 2048, max_w: int = 2048, max_tiles: int | None = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ecseg_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        torch.cuda.init()
+        if max_tiles is None:
+            max_tiles = len(tile_grid(max(max_h, 256), max(max_w, 256))[0])
+        self.max_h, self.max_w, self.max_tiles = max_h, max_w, max_tiles
+        ctx = c_void_p()
+        rc = self.lib.ecseg_ctx_create(byref(ctx), device, max_h, max_w, max_tiles)
+        if rc != 0:
+            raise _lib.EcsegError(rc, "ecseg_ctx_create failed (out of memory or no such device)")
+        self.ctx = ctx
+        self.precision = None
+
+    # -- lifetime -------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.ecseg_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        _lib.check(self.ctx, rc)
+
+    @staticmethod
+    def _stream():
+        return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _dev(self, a, dtype=None) -> torch.Tensor:
+        if isinstance(a, torch.Tensor):
+            t = a.to(self.device)
+        else:
+            a = np.ascontiguousarray(a)
+            if a.dtype == np.uint16:       # torch has limited uint16 support: move raw bytes
+                t = torch.from_numpy(a.view(np.int16)).to(self.device)
+            else:
+                t = torch.from_numpy(a).to(self.device)
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        return t.contiguous()
+
+    # -- model ----------------------------------------------------------------------------------
+    def load_weights(self, w: dict, precision: str = "fp16"):
+        blob = wmod.pack_blob(w)
+        assert blob.size == spec.n_weight_floats()
+        self._chk(self.lib.ecseg_load_weights(self.ctx, blob.ctypes.data_as(c_void_p), blob.size,
+                                              PRECISIONS[precision]))
+        self.precision = precision
+
+    def debug_set(self, stop_after=-1, tc_pitch=0, tc_desc_mode=-1, tc_ntile_max=0):
+        self._chk(self.lib.ecseg_debug_set(self.ctx, stop_after, tc_pitch, tc_desc_mode, tc_ntile_max))
+
+    def device_error(self) -> int:
+        code = c_int()
+        self._chk(self.lib.ecseg_device_error(self.ctx, byref(code)))
+        return code.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.ecseg_launch_count(self.ctx))
+
+    # -- stages (device tensors in / out) -------------------------------------------------------
+    def preprocess(self, img) -> tuple:
+        """meta_preprocess: returns (pre uint8 [H,W], dapi uint8 [H,W]) device tensors."""
+        a = img if isinstance(img, torch.Tensor) else np.asarray(img)
+        h, w = a.shape[:2]
+        ch = 1 if a.ndim == 2 else a.shape[2]
+        bps = 2 if (a.dtype in (np.uint16, torch.int16, torch.uint16)) else 1
+        d = self._dev(a)
+        pre = torch.empty((h, w), dtype=torch.uint8, device=self.device)
+        dapi = torch.empty_like(pre)
+        self._chk(self.lib.ecseg_preprocess(self.ctx, d.data_ptr(), h, w, ch, bps, pre.data_ptr(), dapi.data_ptr(),
+                                            self._stream()))
+        return pre, dapi
+
+    def tile(self, pre: torch.Tensor) -> torch.Tensor:
+        h, w = pre.shape
+        n = len(tile_grid(h, w)[0])
+        tiles = torch.empty((n, 256, 256), dtype=torch.uint8, device=self.device)
+        self._chk(self.lib.ecseg_tile(self.ctx, pre.data_ptr(), h, w, tiles.data_ptr(), self._stream()))
+        return tiles
+
+    def unet_forward(self, tiles, want_logits: bool = False):
+        t = self._dev(tiles, torch.uint8).reshape(-1, 256, 256)
+        n = t.shape[0]
+        probs = torch.empty((n, 256, 256, 4), dtype=torch.float32, device=self.device)
+        logits = torch.empty_like(probs) if want_logits else None
+        self._chk(self.lib.ecseg_unet_forward(self.ctx, t.data_ptr(), n, probs.data_ptr(),
+                                              logits.data_ptr() if want_logits else None, self._stream()))
+        return (probs, logits) if want_logits else probs
+
+    def layer_output(self, layer: int, n: int) -> torch.Tensor:
+        name, kind, cin, cout, relu, bias, level = spec.UNET_LAYERS[layer]
+        hw = 256 >> level
+        out = torch.empty((n, hw, hw, cout), dtype=torch.float32, device=self.device)
+        self._chk(self.lib.ecseg_debug_layer_output(self.ctx, layer, n, out.data_ptr(), self._stream()))
+        return out
+
+    def stitch_argmax(self, probs, h: int, w: int) -> torch.Tensor:
+        p = self._dev(probs, torch.float32)
+        labels = torch.empty((h, w), dtype=torch.uint8, device=self.device)
+        self._chk(self.lib.ecseg_stitch_argmax(self.ctx, p.data_ptr(), h, w, labels.data_ptr(), self._stream()))
+        return labels
+
+    def postprocess(self, labels, faithful_merge: bool = False):
+        """meta_inference + count_cc(I==3): returns (labels uint8 device tensor, n_ec, ec_px)."""
+        lab = self._dev(labels, torch.uint8).clone()
+        h, w = lab.shape
+        n = torch.zeros(1, dtype=torch.int32, device=self.device)
+        px = torch.zeros(1, dtype=torch.int64, device=self.device)
+        flags = PP_FAITHFUL_MERGE if faithful_merge else 0
+        self._chk(self.lib.ecseg_postprocess(self.ctx, lab.data_ptr(), h, w, flags, n.data_ptr(), px.data_ptr(),
+                                             self._stream()))
+        return lab, int(n.item()), int(px.item())
+
+    def count_cc(self, mask):
+        m = self._dev(np.asarray(mask).astype(np.uint8) if not isinstance(mask, torch.Tensor) else mask, torch.uint8)
+        h, w = m.shape
+        n = torch.zeros(1, dtype=torch.int32, device=self.device)
+        px = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._chk(self.lib.ecseg_count_cc(self.ctx, m.data_ptr(), h, w, n.data_ptr(), px.data_ptr(), self._stream()))
+        return int(n.item()), int(px.item())
+
+    def _inplace(self, fn, labels, *args):
+        lab = self._dev(labels, torch.uint8).clone()
+        h, w = lab.shape
+        self._chk(fn(self.ctx, lab.data_ptr(), h, w, *args, self._stream()))
+        return lab
+
+    def fill_holes(self, labels, class_id: int):
+        return self._inplace(self.lib.ecseg_fill_holes, labels, class_id)
+
+    def size_thresh(self, labels):
+        return self._inplace(self.lib.ecseg_size_thresh, labels)
+
+    def merge_comp(self, labels, class_id: int):
+        return self._inplace(self.lib.ecseg_merge_comp, labels, class_id)
+
+    def label(self, mask, connectivity: int = 8) -> torch.Tensor:
+        m = self._dev(mask, torch.uint8)
+        h, w = m.shape
+        out = torch.empty((h, w), dtype=torch.int32, device=self.device)
+        self._chk(self.lib.ecseg_label(self.ctx, m.data_ptr(), h, w, connectivity, out.data_ptr(), self._stream()))
+        return out
+
+    # -- whole image ----------------------------------------------------------------------------
+    def segment_device(self, img: torch.Tensor, h: int, w: int, ch: int, bps: int, faithful_merge=False):
+        """Device-resident path: returns (labels, dapi, n_ec tensor, ec_px tensor) without syncing."""
+        labels = torch.empty((h, w), dtype=torch.uint8, device=self.device)
+        dapi = torch.empty_like(labels)
+        n = torch.zeros(1, dtype=torch.int32, device=self.device)
+        px = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._chk(self.lib.ecseg_segment_image(self.ctx, img.data_ptr(), h, w, ch, bps, dapi.data_ptr(),
+                                               labels.data_ptr(), n.data_ptr(), px.data_ptr(),
+                                               PP_FAITHFUL_MERGE if faithful_merge else 0, self._stream()))
+        return labels, dapi, n, px
+
+    def segment_host(self, img: np.ndarray, labels_out: np.ndarray | None = None, dapi_out: np.ndarray | None = None,
+                     faithful_merge=False):
+        """Host buffers in / out through ecseg_segment_image_host (the end-to-end call)."""
+        img = np.ascontiguousarray(img)
+        h, w = img.shape[:2]
+        ch = 1 if img.ndim == 2 else img.shape[2]
+        bps = img.dtype.itemsize
+        if labels_out is None:
+            labels_out = np.empty((h, w), np.uint8)
+        n, px = c_int32(), c_int64()
+        self._chk(self.lib.ecseg_segment_image_host(
+            self.ctx, img.ctypes.data_as(c_void_p), h, w, ch, bps,
+            dapi_out.ctypes.data_as(c_void_p) if dapi_out is not None else None,
+            labels_out.ctypes.data_as(c_void_p), byref(n), byref(px), PP_FAITHFUL_MERGE if faithful_merge else 0))
+        return labels_out, n.value, px.value
+
+    def last_stage_ms(self):
+        ms = (c_float * 4)()
+        self._chk(self.lib.ecseg_last_stage_ms(self.ctx, ms))
+        return list(ms)

@@ -1,0 +1,82 @@
+"""Drop-in for the metaseg part of the reference's src/image_tools.py: same function names,
+argument meaning and return types, computed by libecseg_b200 on the GPU.
+
+    reference function (src/image_tools.py)        C ABI entry point
+    meta_preprocess            :86-96              ecseg_preprocess
+    im2patches_overlap         :148-186            ecseg_tile / ecseg_tile_grid
+    patches2im_overlap + img_as_ubyte + argmax     ecseg_stitch_argmax   (stitch_argmax below)
+    meta_inference             :15-84              ecseg_postprocess
+    count_cc                   :114-119            ecseg_count_cc
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import spec
+from .engine import Engine, tile_grid
+
+NUM_CLASSES = spec.NUM_CLASSES
+EC_SIZE_THRESHOLD = spec.EC_SIZE_THRESHOLD
+
+_engine = None
+
+
+def default_engine(max_h: int = 2048, max_w: int = 2048) -> Engine:
+    """Process-wide engine on the current CUDA device, grown on demand."""
+    global _engine
+    if _engine is None or _engine.max_h * _engine.max_w < max_h * max_w or \
+            _engine.max_tiles < len(tile_grid(max(max_h, 256), max(max_w, 256))[0]):
+        keep = None
+        if _engine is not None:
+            keep = (_engine._weights, _engine.precision) if getattr(_engine, "_weights", None) else None
+            _engine.close()
+        _engine = Engine(0, max(max_h, 256), max(max_w, 256))
+        if keep:
+            _engine.load_weights(*keep)
+            _engine._weights = keep[0]
+    return _engine
+
+
+def meta_preprocess(img: np.ndarray) -> np.ndarray:
+    """uint8/uint16, gray or RGB(A) -> uint8 [H,W] with dark background (reference :86-96)."""
+    eng = default_engine(*img.shape[:2])
+    pre, _ = eng.preprocess(img)
+    return pre.cpu().numpy()
+
+
+def im2patches_overlap(img: np.ndarray, overlap_value: int = 25, scw: int = 256):
+    """[img, list of 256x256(x1) tiles, list of [row, col] origins] (reference :148-186)."""
+    if overlap_value != spec.OVERLAP or scw != spec.TILE:
+        raise ValueError("the metaseg path is fixed at overlap_value=25, scw=256")
+    a = img[..., 0] if img.ndim == 3 else img
+    eng = default_engine(*a.shape)
+    tiles = eng.tile(eng._dev(a)).cpu().numpy()
+    pos, _, _ = tile_grid(*a.shape)
+    if img.ndim == 3:
+        tiles = tiles[..., None]
+    return [img, list(tiles), [list(map(int, p)) for p in pos]]
+
+
+def stitch_argmax(preds, L_pos=None, shape=None) -> np.ndarray:
+    """patches2im_overlap (:188-252) + img_as_ubyte + np.argmax (src/utils.py:116-118), fused:
+    float32 [N,256,256,4] -> int64 [H,W].  Raises ValueError like img_as_ubyte when a value is
+    outside [-1, 1]."""
+    if shape is None:
+        pos = np.asarray(L_pos)
+        shape = (int(pos[:, 0].max()) + spec.TILE, int(pos[:, 1].max()) + spec.TILE)
+    eng = default_engine(*shape)
+    return eng.stitch_argmax(np.asarray(preds, np.float32), *shape).cpu().numpy().astype(np.int64)
+
+
+def meta_inference(img: np.ndarray) -> np.ndarray:
+    """Post-process a 4-class label map IN PLACE and return it (reference :15-84)."""
+    eng = default_engine(*img.shape)
+    out, _, _ = eng.postprocess(img.astype(np.uint8))
+    img[...] = out.cpu().numpy().astype(img.dtype)
+    return img
+
+
+def count_cc(I: np.ndarray):
+    """(number of 8-connected components, pixel total) of a boolean mask (reference :114-119)."""
+    eng = default_engine(*I.shape)
+    return eng.count_cc(np.asarray(I) != 0)

@@ -25,7 +25,12 @@ from .spec import BN_EPS, NUM_CLASSES, UNET_LAYERS
 # seed -> (per-class gain on the final kernel, per-class offset injected through the constant
 # hidden channel).  Produced once by tools/calibrate_head.py with the CPU oracle on
 # synth.synth_dapi(seed=1000, 512x512); frozen here so every machine builds bit-identical weights.
-HEAD_CALIBRATION = {}
+HEAD_CALIBRATION = {
+    (0, True): ([2.9478561878204346, 1.082884669303894, 1.4067955017089844, 1.6996512413024902],
+                [2.6667776107788086, 2.9298617839813232, -6.335672855377197, 2.4770777225494385]),
+    (0, False): ([2.534174919128418, 5.407772541046143, 1.8347172737121582, 5.1197896003723145],
+                 [0.7570974230766296, -1.771210789680481, -2.018631935119629, -3.137446403503418]),
+}
 
 CONST_CHANNEL = 63  # hidden channel of conv1-4 forced to the constant 1.0 (acts as the head's bias)
 

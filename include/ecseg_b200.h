@@ -1,0 +1,151 @@
+/*
+ * ecseg_b200.h -- C ABI of libecseg_b200.so: the B200-native (sm_100a) implementation of the
+ * metaphase-segmentation hot path of UCRajkumar/ecSeg.
+ *
+ * The reference has no FFI of its own: the path sits behind Python functions
+ * (SURVEY.md section 8b).  Every entry point below therefore names the reference Python function
+ * (file:line under /root/reference) it replaces; ecseg_b200/image_tools.py and ecseg_b200/utils.py
+ * bind them through ctypes under the reference's own function names.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as void* (NULL = default).
+ *   - d_* pointers are device memory owned by the caller, h_* pointers are host memory.
+ *   - all d_* calls are asynchronous on `stream`; results are valid after the caller syncs it.
+ *   - return 0 on success, a negative ECSEG_E_* code otherwise; ecseg_last_error(ctx) gives text.
+ *   - a context is bound to one GPU and is not re-entrant (one per GPU / host thread).
+ *   - label maps are uint8 [H,W] with 0 background, 1 nucleus, 2 chromosome, 3 ecDNA.
+ */
+#ifndef ECSEG_B200_H
+#define ECSEG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ecseg_ctx ecseg_ctx;
+
+#define ECSEG_OK 0
+#define ECSEG_E_INVALID (-1) /* bad argument (shape, dtype, null pointer) */
+#define ECSEG_E_CUDA (-2)    /* CUDA runtime / driver error, text in ecseg_last_error */
+#define ECSEG_E_STATE (-3)   /* call order (e.g. forward before load_weights) */
+#define ECSEG_E_RANGE (-4)   /* img_as_ubyte range violation: a probability outside [-1, 1] */
+#define ECSEG_E_DEVICE (-5)  /* a kernel reported a device-side failure (pipeline watchdog) */
+
+/* arithmetic of the U-Net (ecseg_load_weights `precision`) */
+#define ECSEG_PREC_FP32 0 /* CUDA-core fp32 FMA convolutions: parity mode (logits within 1e-3) */
+#define ECSEG_PREC_BF16 1 /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM */
+#define ECSEG_PREC_FP16 2 /* tcgen05 kind::f16, fp16 operands, fp32 accumulate in TMEM */
+
+/* ecseg_postprocess / ecseg_segment_image flags */
+#define ECSEG_PP_FAITHFUL_MERGE 1 /* also run merge_comp x2 (a proven no-op at that position) */
+
+/* ---- lifetime ----------------------------------------------------------------------------- */
+
+/* Workspace for images up to max_h x max_w and U-Net batches up to max_tiles tiles.
+ * max_tiles == 0 skips the U-Net workspace (post-processing-only context). */
+int ecseg_ctx_create(ecseg_ctx** out, int device, int max_h, int max_w, int max_tiles);
+void ecseg_ctx_destroy(ecseg_ctx* ctx);
+const char* ecseg_last_error(ecseg_ctx* ctx);
+const char* ecseg_version(void);
+
+/* Replaces utils.load_model (src/utils.py:27-33 -> tf.keras.models.load_model).  `blob` is the
+ * flat fp32 array of ecseg_b200.weights.pack_blob (Keras layouts, per layer: kernel, bias, bn flag,
+ * gamma, beta, mean, var).  Folds BatchNorm into kernel/bias, converts to `precision`, packs into
+ * the [tap][Cout][Cin] device layout and builds the TMA descriptors.  Host pointer, synchronous. */
+int ecseg_load_weights(ecseg_ctx* ctx, const float* blob, size_t n_floats, int precision);
+
+/* ---- tile / stitch front end -------------------------------------------------------------- */
+
+/* Tile grid of im2patches_overlap (src/image_tools.py:148-186): 256x256 tiles, 25-px overlap.
+ * pos (nullable) receives n_tiles x 2 (row, col) origins in the reference's order. Host only. */
+int ecseg_tile_grid(int h, int w, int* n_tiles, int* n_rows, int* n_cols, int32_t* pos);
+
+/* Replaces image_tools.meta_preprocess + u16_to_u8 (src/image_tools.py:86-101) and the
+ * cv2.bitwise_not feeding utils.save_img (src/utils.py:112).
+ * d_img: [h,w] or [h,w,ch] interleaved (RGB order, ch in {1,3,4}); bytes_per_sample 1 or 2.
+ * d_pre: uint8 [h,w] pre-processed image; d_dapi (nullable): uint8 [h,w] = 255 - d_pre. */
+int ecseg_preprocess(ecseg_ctx* ctx, const void* d_img, int h, int w, int ch, int bytes_per_sample,
+                     uint8_t* d_pre, uint8_t* d_dapi, void* stream);
+
+/* Replaces image_tools.im2patches_overlap (src/image_tools.py:148-186): d_tiles uint8
+ * [n_tiles,256,256]. */
+int ecseg_tile(ecseg_ctx* ctx, const uint8_t* d_pre, int h, int w, uint8_t* d_tiles, void* stream);
+
+/* Replaces model.predict_on_batch (call site src/utils.py:115; topology template
+ * src/model_layers/models.py:17-136): uint8 [n,256,256,1] raw 0..255 -> softmax probabilities
+ * float32 [n,256,256,4].  d_logits (nullable) receives the pre-softmax values, same shape. */
+int ecseg_unet_forward(ecseg_ctx* ctx, const uint8_t* d_tiles, int n, float* d_probs, float* d_logits,
+                       void* stream);
+
+/* Replaces image_tools.patches2im_overlap (src/image_tools.py:188-252, including the region its
+ * strip writers never reach) + skimage.img_as_ubyte + np.argmax (src/utils.py:117-118):
+ * float32 [n_tiles,256,256,4] -> uint8 labels [h,w]. */
+int ecseg_stitch_argmax(ecseg_ctx* ctx, const float* d_probs, int h, int w, uint8_t* d_labels, void* stream);
+
+/* ---- post-processing ---------------------------------------------------------------------- */
+
+/* Replaces image_tools.meta_inference (src/image_tools.py:15-84) followed by
+ * image_tools.count_cc(I==3) (src/image_tools.py:114-119, call site src/metaseg.py:46).
+ * d_labels is updated in place; d_n_ec / d_ec_px (device, nullable) receive the count tuple. */
+int ecseg_postprocess(ecseg_ctx* ctx, uint8_t* d_labels, int h, int w, int flags, int32_t* d_n_ec,
+                      int64_t* d_ec_px, void* stream);
+
+/* Replaces image_tools.count_cc (src/image_tools.py:114-119): 8-connected components of a
+ * non-zero mask; returns (count, pixel total) including the reference's np.unique()[1:] quirk. */
+int ecseg_count_cc(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w, int32_t* d_n, int64_t* d_px,
+                   void* stream);
+
+/* The nested helpers of meta_inference, exposed for step-level parity tests. In place. */
+int ecseg_fill_holes(ecseg_ctx* ctx, uint8_t* d_labels, int h, int w, int class_id, void* stream); /* :36-39 */
+int ecseg_size_thresh(ecseg_ctx* ctx, uint8_t* d_labels, int h, int w, void* stream);               /* :41-59 */
+int ecseg_merge_comp(ecseg_ctx* ctx, uint8_t* d_labels, int h, int w, int class_id, void* stream);  /* :18-33 */
+
+/* 8- or 4-connected labelling of the non-zero pixels of d_mask (components of equal value):
+ * d_out int32 [h,w], 0 background, otherwise 1 + linear index of the component's first pixel. */
+int ecseg_label(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w, int connectivity, int32_t* d_out,
+                void* stream);
+
+/* ---- whole image -------------------------------------------------------------------------- */
+
+/* Replaces utils.meta_segment (src/utils.py:109-120) minus file I/O, plus count_cc(I==3):
+ * raw image -> pre-process -> tiles -> U-Net -> stitch/quantise/argmax -> meta_inference -> count.
+ * Tiles, activations and probabilities never leave the GPU.  Outputs (device): d_dapi uint8 [h,w]
+ * (nullable), d_labels uint8 [h,w], d_n_ec int32, d_ec_px int64. */
+int ecseg_segment_image(ecseg_ctx* ctx, const void* d_img, int h, int w, int ch, int bytes_per_sample,
+                        uint8_t* d_dapi, uint8_t* d_labels, int32_t* d_n_ec, int64_t* d_ec_px, int flags,
+                        void* stream);
+
+/* Same with HOST buffers: copies the image in, runs the path, copies labels / dapi / counts out and
+ * synchronises.  h_img should be pinned for full copy bandwidth.  This is the call the
+ * reference-facing Python shim and bench.py's end-to-end number go through. */
+int ecseg_segment_image_host(ecseg_ctx* ctx, const void* h_img, int h, int w, int ch, int bytes_per_sample,
+                             uint8_t* h_dapi, uint8_t* h_labels, int32_t* n_ec, int64_t* ec_px, int flags);
+
+/* ---- introspection used by tests and bench.py ----------------------------------------------- */
+
+/* Copy the activation a U-Net layer produced in the last forward as float32 NHWC
+ * [n, H_l, W_l, C_l] (layer index per ecseg_b200.spec.UNET_LAYERS). */
+int ecseg_debug_layer_output(ecseg_ctx* ctx, int layer, int n, float* d_out, void* stream);
+
+/* Debug knobs: stop the U-Net forward after `stop_after_layer` (-1 = run everything) and select the
+ * tcgen05 kernel variant (halo pitch 18|24, descriptor base-offset mode 0|1, max N tile 64|128|256);
+ * values outside those sets leave the setting unchanged. */
+int ecseg_debug_set(ecseg_ctx* ctx, int stop_after_layer, int tc_pitch, int tc_desc_mode, int tc_ntile_max);
+
+/* Synchronise and read the device-side pipeline watchdog flag (0 = healthy). */
+int ecseg_device_error(ecseg_ctx* ctx, int* code);
+
+/* Number of kernels this library launched on behalf of ctx since creation. */
+int64_t ecseg_launch_count(ecseg_ctx* ctx);
+
+/* Per-stage device time of the last ecseg_segment_image* call (CUDA events on the call's stream):
+ * ms[0] pre-process+tiling, ms[1] U-Net, ms[2] stitch, ms[3] post-processing.  Synchronises. */
+int ecseg_last_stage_ms(ecseg_ctx* ctx, float ms[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECSEG_B200_H */
