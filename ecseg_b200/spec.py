@@ -1,7 +1,7 @@
 """Fixed constants and the U-Net architecture table of the metaseg hot path.
 
 Everything here is plain data shared by the CUDA host code, the weight generator and the
-CPU oracle.  Sources in the reference (paths relative to /root/reference):
+CPU checker (tests only).  Sources in the reference (paths relative to /root/reference):
 
 * NUM_CLASSES, EC_SIZE_THRESHOLD ........ src/image_tools.py:12-13
 * OVERLAP, TILE ........................... src/image_tools.py:148,188 (overlap_value=25, scw=256)
