@@ -40,6 +40,7 @@ int ecseg_ctx_create(ecseg_ctx** out, int device, int max_h, int max_w, int max_
   ecseg_ctx* ctx = new (std::nothrow) ecseg_ctx();
   if (!ctx) return ECSEG_E_INVALID;
   ctx->device = device;
+  cudaDeviceGetAttribute(&ctx->n_sms, cudaDevAttrMultiProcessorCount, device);
   ctx->max_h = max_h; ctx->max_w = max_w; ctx->max_tiles = max_tiles;
   ctx->max_px = (size_t)max_h * max_w;
   const size_t P = ctx->max_px;

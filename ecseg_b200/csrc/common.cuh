@@ -59,6 +59,7 @@ struct UNet;  // unet.cu
 
 struct ecseg_ctx {
   int device = 0;
+  int n_sms = 148;
   int max_h = 0, max_w = 0, max_tiles = 0;
   size_t max_px = 0;
   std::string err;

@@ -23,129 +23,16 @@
 // Pipelines are mbarrier based (full/empty per A stage, per B stage, per accumulator stage).
 #include "conv_tc.cuh"
 #include "stitch.cuh"
+#include "tc_common.cuh"
 
 namespace ecseg {
 
 namespace {
 
+using namespace tc;
+
 constexpr int kThreads = 256;
 constexpr int kEpiWarp0 = 4;
-constexpr long long kWatchdogCycles = 4000000000ll;  // ~2 s: a stuck pipeline reports instead of hanging
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok;
-}
-// Bounded wait: returns false (and raises the device error flag) instead of hanging forever.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
-  if (mbar_try_wait(bar, parity)) return true;
-  const long long t0 = clock64();
-  unsigned spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 255u) == 0) {
-      if (clock64() - t0 > kWatchdogCycles || *(volatile int*)err_flag != 0) {
-        atomicCAS(err_flag, 0, code);
-        return false;
-      }
-    }
-  }
-  return true;
-}
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// tcgen05.commit: the mbarrier receives one arrival when all previously issued MMAs have completed.
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16/fp16 operands, fp32 accumulate.
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-// Shared-memory matrix descriptor, K-major operand, SWIZZLE_128B: rows are 128 B apart inside an
-// 8-row group, groups are `sbo` bytes apart.
-__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t sbo, uint32_t base_off) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
-  d |= (uint64_t)1u << 16;                       // leading byte offset: unused for swizzled K-major (canonical 1)
-  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;   // stride byte offset
-  d |= (uint64_t)1u << 46;                       // descriptor version: Blackwell
-  d |= (uint64_t)(base_off & 7u) << 49;
-  d |= (uint64_t)2u << 61;                       // SWIZZLE_128B
-  return d;
-}
-
-// Instruction descriptor, kind::f16: fp32 accumulate, A/B both K-major.
-__device__ __forceinline__ uint32_t make_idesc(int m, int n, int bf16) {
-  uint32_t d = 0;
-  d |= 1u << 4;                          // D format F32
-  d |= (uint32_t)(bf16 ? 1 : 0) << 7;    // A format (0 F16, 1 BF16)
-  d |= (uint32_t)(bf16 ? 1 : 0) << 10;   // B format
-  d |= (uint32_t)(n >> 3) << 17;
-  d |= (uint32_t)(m >> 4) << 24;
-  return d;
-}
-
-// 32 lanes x 16 consecutive columns of fp32 accumulators -> 16 registers per thread.
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ uint32_t pack2(float a, float b, int bf16) {
-  if (bf16) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-  }
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
 
 template <int N_TILE, int PITCH>
 struct Cfg {
@@ -163,7 +50,7 @@ struct Cfg {
   static constexpr int kSmemBytes = kAStages * kAStride + kBStages * kBStride + kNumBars * 8 + 16 + 1024;
 };
 
-template <int N_TILE, int PITCH, bool HEAD>
+template <int N_TILE, int PITCH>
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__ ConvTcParams p) {
   using C = Cfg<N_TILE, PITCH>;
   extern __shared__ uint8_t smem_raw[];
@@ -301,25 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int y = y0 + r, x = x0 + half * 8 + c;
-        if (HEAD) {
-          uint32_t v[16];
-          tmem_ld16(t0 + half * N_TILE, v);
-          tmem_ld_wait();
-          float z[4], pr[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) z[j] = __uint_as_float(v[j]);
-          softmax4(z, pr);
-          const size_t pix = ((size_t)img * kTile + y) * kTile + x;
-          if (p.logits) reinterpret_cast<float4*>(p.logits)[pix] = make_float4(z[0], z[1], z[2], z[3]);
-          if (p.probs) reinterpret_cast<float4*>(p.probs)[pix] = make_float4(pr[0], pr[1], pr[2], pr[3]);
-          if (p.labels) {
-            int err = 0;
-            const int lab = quantised_argmax(pr[0], pr[1], pr[2], pr[3], &err);
-            stitch_write_owned(p.grid, img, y, x, lab, p.labels);
-          }
-          if (p.debug_dump && blockIdx.x == 0 && wk == blockIdx.x)
-            for (int j = 0; j < 16; ++j) p.debug_dump[(half * 128 + m) * N_TILE + j] = __uint_as_float(v[j]);
-        } else {
+        {
           const int oy = y * p.oscale + p.par_oy[par], ox = x * p.oscale + p.par_ox[par];
           uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) +
                           (((size_t)img * p.out_H + oy) * p.out_W + ox) * p.out_pitch + p.out_choff + nch * N_TILE;
@@ -344,6 +213,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
             o1.z = pack2(f[12], f[13], p.is_bf16); o1.w = pack2(f[14], f[15], p.is_bf16);
             *reinterpret_cast<uint4*>(dst + c0) = o0;
             *reinterpret_cast<uint4*>(dst + c0 + 8) = o1;
+            if (p.pool_out) {
+              // fused 2x2/2 max pool (models.py:28,40,52,64): the 2x2 window of pixel (r, c) lives in
+              // lanes ^1 (x neighbour) and ^8 (y neighbour); max commutes with the monotone rounding.
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
+                f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 8));
+              }
+              if ((lane & 9) == 0) {
+                uint16_t* pd = reinterpret_cast<uint16_t*>(p.pool_out) +
+                               (((size_t)img * (p.out_H >> 1) + (y >> 1)) * (p.out_W >> 1) + (x >> 1)) * p.pool_pitch +
+                               nch * N_TILE + c0;
+                o0.x = pack2(f[0], f[1], p.is_bf16);  o0.y = pack2(f[2], f[3], p.is_bf16);
+                o0.z = pack2(f[4], f[5], p.is_bf16);  o0.w = pack2(f[6], f[7], p.is_bf16);
+                o1.x = pack2(f[8], f[9], p.is_bf16);  o1.y = pack2(f[10], f[11], p.is_bf16);
+                o1.z = pack2(f[12], f[13], p.is_bf16); o1.w = pack2(f[14], f[15], p.is_bf16);
+                *reinterpret_cast<uint4*>(pd) = o0;
+                *reinterpret_cast<uint4*>(pd + 8) = o1;
+              }
+            }
           }
         }
       }
@@ -362,17 +251,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
   }
 }
 
-template <int N_TILE, int PITCH, bool HEAD>
+template <int N_TILE, int PITCH>
 int launch_cfg(ecseg_ctx* ctx, const ConvTcParams& p, cudaStream_t st) {
   using C = Cfg<N_TILE, PITCH>;
-  auto kern = k_conv_tc<N_TILE, PITCH, HEAD>;
+  auto kern = k_conv_tc<N_TILE, PITCH>;
   static bool attr_done = false;
   if (!attr_done) {
     ECSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_done = true;
   }
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const int sms = ctx->n_sms;
   const int n_work = p.n_img * (p.H >> 4) * (p.W >> 4) * p.n_par * p.n_chunks;
   const int grid = n_work < sms ? n_work : sms;
   kern<<<grid, kThreads, C::kSmemBytes, st>>>(p);
@@ -382,26 +270,23 @@ int launch_cfg(ecseg_ctx* ctx, const ConvTcParams& p, cudaStream_t st) {
 
 }  // namespace
 
-int conv_tc_launch(ecseg_ctx* ctx, const ConvTcParams& p, int n_tile, int pitch, bool head, cudaStream_t st) {
+int conv_tc_launch(ecseg_ctx* ctx, const ConvTcParams& p, int n_tile, int pitch, cudaStream_t st) {
   if ((p.H & 15) || (p.W & 15) || p.cin_chunks < 1 || p.n_chunks < 1) {
     ctx->err = "conv_tc: H, W must be multiples of 16 and Cin a multiple of 64";
     return ECSEG_E_INVALID;
   }
-  if (head) {
-    if (n_tile != 16) { ctx->err = "conv_tc: head needs N_TILE 16"; return ECSEG_E_INVALID; }
-    return pitch == 18 ? launch_cfg<16, 18, true>(ctx, p, st) : launch_cfg<16, 24, true>(ctx, p, st);
-  }
+  if (p.pool_out && p.oscale != 1) { ctx->err = "conv_tc: pool fusion needs a plain convolution"; return ECSEG_E_INVALID; }
   if (pitch == 18) {
     switch (n_tile) {
-      case 64: return launch_cfg<64, 18, false>(ctx, p, st);
-      case 128: return launch_cfg<128, 18, false>(ctx, p, st);
-      case 256: return launch_cfg<256, 18, false>(ctx, p, st);
+      case 64: return launch_cfg<64, 18>(ctx, p, st);
+      case 128: return launch_cfg<128, 18>(ctx, p, st);
+      case 256: return launch_cfg<256, 18>(ctx, p, st);
     }
   } else if (pitch == 24) {
     switch (n_tile) {
-      case 64: return launch_cfg<64, 24, false>(ctx, p, st);
-      case 128: return launch_cfg<128, 24, false>(ctx, p, st);
-      case 256: return launch_cfg<256, 24, false>(ctx, p, st);
+      case 64: return launch_cfg<64, 24>(ctx, p, st);
+      case 128: return launch_cfg<128, 24>(ctx, p, st);
+      case 256: return launch_cfg<256, 24>(ctx, p, st);
     }
   }
   ctx->err = "conv_tc: unsupported N_TILE / PITCH";

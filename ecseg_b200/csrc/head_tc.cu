@@ -1,0 +1,201 @@
+// U-Net head for sm_100a: final 3x3 convolution 64 -> 4 classes (no bias, reference template
+// src/model_layers/models.py:134) + softmax + img_as_ubyte quantisation + first-max argmax
+// (src/utils.py:117-118) + stitch ownership write (src/image_tools.py:188-252), one kernel.
+//
+// A 3x3 convolution with only 4 output channels is a poor tensor-core shape (N = 4), and as an
+// implicit GEMM over 9 taps it would read the activation halo from shared memory nine times for
+// almost no math.  The taps are therefore moved into the GEMM's N dimension:
+//     Z[p, t*4 + c] = sum_ci X[p, ci] * W[t, c, ci]          (1x1 GEMM, N = 36 -> 48, K = 64)
+//     logit[y, x, c] = sum_t Z[(y + dy_t, x + dx_t), t*4 + c]  (9-point shifted sum, fp32)
+// so every halo pixel goes through the tensor core exactly once.  Per 16x16 output block:
+//   warp 0 lane 0 : TMA producer -- one 18x18x64 halo load (zero fill outside the tile = 'same'
+//                   padding; with no bias Z is exactly 0 there), rows p = hy*18 + hx, 128 B each,
+//                   SWIZZLE_128B; the 48x64 weight matrix is loaded once per CTA.
+//   warp 1 lane 0 : MMA issuer -- 3 M-tiles (384 >= 324 halo rows) x 4 K-steps of
+//                   tcgen05.mma.cta_group::1.kind::f16 M=128 N=48 K=16 into TMEM (double buffered).
+//   warp 2        : TMEM allocation.
+//   warps 4..7    : epilogue -- tcgen05.ld Z rows -> shared memory [324][37] fp32, then each thread
+//                   sums the 9 taps for 2 output pixels, softmax, quantise, argmax, owned write.
+#include "conv_tc.cuh"
+#include "stitch.cuh"
+#include "tc_common.cuh"
+
+namespace ecseg {
+
+namespace {
+
+using namespace tc;
+
+constexpr int kThreads = 256;
+constexpr int kHalo = 18 * 18;                 // 324 halo pixels
+constexpr int kAStages = 3;
+constexpr int kABytes = kHalo * 128;           // bytes one halo load delivers
+constexpr int kAStride = 3 * 128 * 128;        // 3 M-tiles of 128 rows x 128 B (rows >= 324 are never read back)
+constexpr int kNRows = 48;                     // 9 taps x 4 classes = 36, padded to a legal UMMA N
+constexpr int kBBytes = kNRows * 128;
+constexpr int kBStride = 6 * 1024;
+constexpr int kZPitch = 37;                    // odd pitch: conflict-free column access
+constexpr int kZBytes = kHalo * kZPitch * 4;
+constexpr int kAccCols = 3 * 64;               // 3 M-tiles, 64-column spacing
+constexpr int kTmemCols = 512;                 // 2 accumulator stages x 192 -> next power of two
+constexpr int kNumBars = 2 * kAStages + 1 + 4;
+constexpr int kSmemBytes = kAStages * kAStride + kBStride + kZBytes + kNumBars * 8 + 16 + 1024;
+
+__global__ void __launch_bounds__(kThreads, 1) k_head_tc(const __grid_constant__ HeadTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_base = smem_u32(smem);
+  const uint32_t b_base = a_base + kAStages * kAStride;
+  float* zs = reinterpret_cast<float*>(smem + kAStages * kAStride + kBStride);
+  const uint32_t bar_base = b_base + kBStride + kZBytes;
+  auto full_a = [&](int s) { return bar_base + 8u * s; };
+  auto empty_a = [&](int s) { return bar_base + 8u * (kAStages + s); };
+  const uint32_t full_b = bar_base + 8u * (2 * kAStages);
+  auto tmem_full = [&](int s) { return bar_base + 8u * (2 * kAStages + 1 + s); };
+  auto tmem_empty = [&](int s) { return bar_base + 8u * (2 * kAStages + 3 + s); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kAStages * kAStride + kBStride + kZBytes + kNumBars * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kAStages; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
+    mbar_init(full_b, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_ptr_smem), kTmemCols);
+  } else if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tm_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tm_b) : "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
+
+  constexpr int kBlocksPerImg = (kTile / 16) * (kTile / 16);
+  const int n_work = p.n_img * kBlocksPerImg;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    mbar_expect_tx(full_b, kBBytes);
+    tma_load_2d(b_base, &p.tm_b, full_b, 0, 0);
+    int sa = 0, pa = 0;
+    for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+      const int img = wk / kBlocksPerImg, rem = wk % kBlocksPerImg;
+      const int y0 = (rem / (kTile / 16)) << 4, x0 = (rem % (kTile / 16)) << 4;
+      if (!mbar_wait(empty_a(sa), pa ^ 1, p.device_error, 11)) break;
+      mbar_expect_tx(full_a(sa), kABytes);
+      tma_load_4d(a_base + sa * kAStride, &p.tm_a, full_a(sa), 0, x0 - 1, y0 - 1, img);
+      if (++sa == kAStages) { sa = 0; pa ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc(128, kNRows, p.is_bf16);
+    int sa = 0, pa = 0, as = 0, pacc = 0;
+    bool ok = mbar_wait(full_b, 0, p.device_error, 12);
+    for (int wk = blockIdx.x; wk < n_work && ok; wk += gridDim.x) {
+      ok = mbar_wait(tmem_empty(as), pacc ^ 1, p.device_error, 13);
+      if (!ok) break;
+      ok = mbar_wait(full_a(sa), pa, p.device_error, 14);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t a_stage = a_base + sa * kAStride;
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt) {
+        const uint32_t d = tmem_base + (uint32_t)(as * kAccCols + mt * 64);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t adesc = make_sdesc(a_stage + mt * (128 * 128) + k * 32, 1024, 0);
+          const uint64_t bdesc = make_sdesc(b_base + k * 32, 1024, 0);
+          umma_f16(d, adesc, bdesc, idesc, k > 0);
+        }
+      }
+      umma_commit(empty_a(sa));
+      umma_commit(tmem_full(as));
+      if (++sa == kAStages) { sa = 0; pa ^= 1; }
+      if (++as == 2) { as = 0; pacc ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int te = q * 32 + lane;           // 0..127
+    int as = 0, pacc = 0;
+    for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+      const int img = wk / kBlocksPerImg, rem = wk % kBlocksPerImg;
+      const int y0 = (rem / (kTile / 16)) << 4, x0 = (rem % (kTile / 16)) << 4;
+      if (!mbar_wait(tmem_full(as), pacc, p.device_error, 15)) break;
+      tc_fence_after();
+      // Z rows out of TMEM into shared memory (all 128 epilogue threads finished reading the
+      // previous block's Z: second named barrier below)
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt) {
+        const int j = mt * 128 + te;
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccCols + mt * 64);
+        uint32_t v[32], u[4];
+        tmem_ld32(t0, v);
+        tmem_ld4(t0 + 32, u);
+        tmem_ld_wait();
+        if (j < kHalo) {
+          float* zr = zs + j * kZPitch;
+#pragma unroll
+          for (int n = 0; n < 32; ++n) zr[n] = __uint_as_float(v[n]);
+#pragma unroll
+          for (int n = 0; n < 4; ++n) zr[32 + n] = __uint_as_float(u[n]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty(as));            // accumulator drained: the next block's MMAs may start
+      if (++as == 2) { as = 0; pacc ^= 1; }
+      named_bar_sync(1, 128);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int pi = h * 128 + te;
+        const int ty = pi >> 4, tx = pi & 15;
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float* zr = zs + ((ty + t / 3) * 18 + tx + t % 3) * kZPitch + t * 4;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) z[c] += zr[c];
+        }
+        float pr[4];
+        softmax4(z, pr);
+        const int y = y0 + ty, x = x0 + tx;
+        const size_t pix = ((size_t)img * kTile + y) * kTile + x;
+        if (p.logits) reinterpret_cast<float4*>(p.logits)[pix] = make_float4(z[0], z[1], z[2], z[3]);
+        if (p.probs) reinterpret_cast<float4*>(p.probs)[pix] = make_float4(pr[0], pr[1], pr[2], pr[3]);
+        if (p.labels) {
+          int err = 0;
+          const int lab = quantised_argmax(pr[0], pr[1], pr[2], pr[3], &err);
+          stitch_write_owned(p.grid, img, y, x, lab, p.labels);
+        }
+      }
+      named_bar_sync(1, 128);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+int head_tc_launch(ecseg_ctx* ctx, const HeadTcParams& p, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    ECSEG_CUDA(cudaFuncSetAttribute(k_head_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_done = true;
+  }
+  const int n_work = p.n_img * (kTile / 16) * (kTile / 16);
+  const int grid = n_work < ctx->n_sms ? n_work : ctx->n_sms;
+  k_head_tc<<<grid, kThreads, kSmemBytes, st>>>(p);
+  ECSEG_CHECK_LAUNCH();
+  return ECSEG_OK;
+}
+
+}  // namespace ecseg

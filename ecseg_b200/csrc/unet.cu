@@ -83,6 +83,28 @@ template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v
 // un-normalised, src/utils.py:113-115) either from materialised tiles or straight from the
 // pre-processed image through the tile grid (fused im2patches_overlap).
 // ------------------------------------------------------------------------------------------------
+// 8 consecutive channels of one pixel: one 16-byte store (two for fp32)
+__device__ __forceinline__ void store8(float* dst, const float v[8]) {
+  reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__half* dst, const float v[8]) {
+  __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+  __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+  uint4 o;
+  o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+  o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+  *reinterpret_cast<uint4*>(dst) = o;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* dst, const float v[8]) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 o;
+  o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+  o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+  *reinterpret_cast<uint4*>(dst) = o;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_conv_first(const uint8_t* __restrict__ tiles, const uint8_t* __restrict__ pre,
                                                     TileGrid g, const float* __restrict__ w9x64,
@@ -120,9 +142,9 @@ __global__ void __launch_bounds__(256) k_conv_first(const uint8_t* __restrict__ 
       for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wp[j], acc[j]);
     }
   }
-  T* dst = out + (((size_t)img * kTile + y) * kTile + x) * 64 + cg;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) dst[j] = from_f<T>(fmaxf(acc[j], 0.f));
+  for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+  store8(out + (((size_t)img * kTile + y) * kTile + x) * 64 + cg, acc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -380,8 +402,16 @@ int unet_load_weights(ecseg_ctx* ctx, const float* blob, size_t n_floats, int pr
       ECSEG_CUDA(cudaMalloc(&net->w[li], w.size() * sizeof(float)));
       ECSEG_CUDA(cudaMemcpy(net->w[li], w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
       net->cout_rows[li] = 64;
+    } else if (tc && li == 22) {   // head: [48][64] 16-bit, row = tap*4 + class (head_tc.cu)
+      std::vector<uint16_t> w((size_t)48 * l.cin, 0);
+      for (int t = 0; t < 9; ++t)
+        for (int co = 0; co < l.cout; ++co)
+          for (int ci = 0; ci < l.cin; ++ci) w[((size_t)t * 4 + co) * l.cin + ci] = f2h_bits(kval(t, ci, co), bf16);
+      ECSEG_CUDA(cudaMalloc(&net->w[li], w.size() * 2));
+      ECSEG_CUDA(cudaMemcpy(net->w[li], w.data(), w.size() * 2, cudaMemcpyHostToDevice));
+      net->cout_rows[li] = 48;
     } else if (tc) {   // [tap][cout_rows][cin] 16-bit, K-major rows for TMA / UMMA
-      const int rows = l.cout < 16 ? 16 : l.cout;
+      const int rows = l.cout;
       std::vector<uint16_t> w((size_t)9 * rows * l.cin, 0);
       for (int t = 0; t < 9; ++t)
         for (int co = 0; co < l.cout; ++co)
@@ -462,14 +492,24 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   const LayerDef& l = kLayers[li];
   const Wire& wr = kWires[li];
   const bool bf16 = net->precision == ECSEG_PREC_BF16;
+  if (li == 22) {
+    HeadTcParams h;
+    memset(&h, 0, sizeof(h));
+    ECSEG_TRY(make_tm_act(ctx, &h.tm_a, net->buf[wr.in], l.cin, kBufs[wr.in].ch, kTile, kTile, ctx->max_tiles, 18, bf16));
+    ECSEG_TRY(make_tm_wgt(ctx, &h.tm_b, net->w[li], l.cin, 48, 48, bf16));
+    h.n_img = n; h.is_bf16 = bf16;
+    h.probs = d_probs; h.logits = d_logits; h.labels = d_labels;
+    if (grid) h.grid = *grid;
+    h.device_error = &ctx->counters->device_error;
+    return head_tc_launch(ctx, h, st);
+  }
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
   fill_taps(p, l.convT != 0);
   const int out_hw = kTile >> l.level;
   const int in_hw = l.convT ? out_hw / 2 : out_hw;
-  const bool head = li == 22;
   const int rows = net->cout_rows[li];
-  int n_tile = head ? 16 : (rows < net->tc_ntile_max ? rows : net->tc_ntile_max);
+  int n_tile = rows < net->tc_ntile_max ? rows : net->tc_ntile_max;
   if (n_tile > 256) n_tile = 256;
   ECSEG_TRY(make_tm_act(ctx, &p.tm_a, net->buf[wr.in], l.cin, kBufs[wr.in].ch, in_hw, in_hw, ctx->max_tiles,
                         net->tc_pitch == 18 ? 18 : 1, bf16));
@@ -480,14 +520,10 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   p.desc_mode = net->tc_desc_mode;
   p.device_error = &ctx->counters->device_error;
   p.debug_dump = nullptr;
-  if (head) {
-    p.probs = d_probs; p.logits = d_logits; p.labels = d_labels;
-    if (grid) p.grid = *grid;
-  } else {
-    p.out = net->buf[wr.out]; p.out_H = out_hw; p.out_W = out_hw;
-    p.out_pitch = kBufs[wr.out].ch; p.out_choff = wr.choff;
-  }
-  return conv_tc_launch(ctx, p, n_tile, net->tc_pitch, head, st);
+  p.out = net->buf[wr.out]; p.out_H = out_hw; p.out_W = out_hw;
+  p.out_pitch = kBufs[wr.out].ch; p.out_choff = wr.choff;
+  if (wr.pool_to >= 0) { p.pool_out = net->buf[wr.pool_to]; p.pool_pitch = kBufs[wr.pool_to].ch; }   // fused max pool
+  return conv_tc_launch(ctx, p, n_tile, net->tc_pitch, st);
 }
 
 int unet_forward(ecseg_ctx* ctx, const uint8_t* d_tiles, const uint8_t* d_pre, const TileGrid* grid, int n,
@@ -510,12 +546,8 @@ int unet_forward(ecseg_ctx* ctx, const uint8_t* d_tiles, const uint8_t* d_pre, c
       ECSEG_TRY(run_layer_tc(ctx, li, n, d_probs, d_logits, d_labels, grid, st));
     }
     if (net->stop_after == li) return ECSEG_OK;
-    const int pt = kWires[li].pool_to;
-    if (pt >= 0) {
-      if (prec == ECSEG_PREC_FP32) ECSEG_TRY(run_pool<float>(ctx, kWires[li].out, pt, n, st));
-      else if (prec == ECSEG_PREC_BF16) ECSEG_TRY(run_pool<__nv_bfloat16>(ctx, kWires[li].out, pt, n, st));
-      else ECSEG_TRY(run_pool<__half>(ctx, kWires[li].out, pt, n, st));
-    }
+    const int pt = kWires[li].pool_to;   // tensor-core modes pool inside the conv epilogue
+    if (pt >= 0 && prec == ECSEG_PREC_FP32) ECSEG_TRY(run_pool<float>(ctx, kWires[li].out, pt, n, st));
   }
   return ECSEG_OK;
 }
