@@ -6,7 +6,7 @@
 #include "common.cuh"
 
 namespace ecseg {
-int unet_set_debug(ecseg_ctx* ctx, int stop_after, int tc_pitch, int tc_desc_mode, int tc_ntile_max);
+int unet_set_debug(ecseg_ctx* ctx, int stop_after, int tc_cluster, int tc_ntile_max);
 int fe_zero_counters(ecseg_ctx* ctx, cudaStream_t st);
 }
 
@@ -216,9 +216,9 @@ int ecseg_debug_layer_output(ecseg_ctx* ctx, int layer, int n, float* d_out, voi
   return unet_debug_layer(ctx, layer, n, d_out, (cudaStream_t)stream);
 }
 
-int ecseg_debug_set(ecseg_ctx* ctx, int stop_after_layer, int tc_pitch, int tc_desc_mode, int tc_ntile_max) {
+int ecseg_debug_set(ecseg_ctx* ctx, int stop_after_layer, int tc_cluster, int tc_ntile_max) {
   API_GUARD(ctx);
-  return unet_set_debug(ctx, stop_after_layer, tc_pitch, tc_desc_mode, tc_ntile_max);
+  return unet_set_debug(ctx, stop_after_layer, tc_cluster, tc_ntile_max);
 }
 
 int ecseg_device_error(ecseg_ctx* ctx, int* code) {

@@ -1,28 +1,33 @@
 // tcgen05 / TMEM / TMA implicit-GEMM 3x3 convolution for sm_100a.
 //
-// Replaces the Keras Conv2D / Conv2DTranspose (+BatchNorm +ReLU) layers the reference runs inside
-// model.predict_on_batch (call site src/utils.py:115; topology template
+// Replaces the Keras Conv2D / Conv2DTranspose (+BatchNorm +ReLU +MaxPool) layers the reference runs
+// inside model.predict_on_batch (call site src/utils.py:115; topology template
 // src/model_layers/models.py:17-136).
 //
-// One persistent CTA per SM, 8 warps:
+// One persistent CTA per SM, 8 warps, optionally paired into clusters of 2:
 //   warp 0 lane 0 : TMA producer.  Per (M block, 64-channel chunk) ONE halo load of the 18x18
 //                   pixel neighbourhood of a 16x16 output block (TMA zero-fills outside the image
 //                   tile = Keras 'same' padding), and per (chunk, tap) one weight tile
 //                   [N_TILE x 64].  The 9 taps are 9 shifted VIEWS of the same halo in shared
-//                   memory (descriptor start address + (dy*PITCH+dx)*128 B), so activations cross
-//                   L2 -> SM once instead of nine times.
+//                   memory (descriptor start address + (dy*18+dx)*128 B), so activations cross
+//                   L2 -> SM once instead of nine times.  In a cluster each CTA fetches 1/CS of
+//                   every weight tile and multicasts it to all CTAs of the cluster (the CTAs work
+//                   on different M blocks of the same output-channel chunk in lock step), which
+//                   divides the L2 -> SM weight traffic by CS.
 //   warp 1 lane 0 : MMA issuer.  tcgen05.mma.cta_group::1.kind::f16, M=128 x N=N_TILE x K=16,
 //                   two M halves (left / right 8 columns of the 16x16 block) share every weight
-//                   stage; fp32 accumulators live in TMEM (2 x N_TILE columns per stage, double
-//                   buffered when 4*N_TILE <= 512).
+//                   stage; fp32 accumulators live in TMEM (2 x NACC x N_TILE columns per stage,
+//                   double buffered when that fits twice into the 512 columns).  For a transposed
+//                   convolution the 9 taps are routed to NACC = 4 accumulators, one per output
+//                   parity, so the halo is loaded once for all four.
 //   warp 2        : TMEM allocation / deallocation.
-//   warps 4..7    : epilogue.  tcgen05.ld -> bias -> ReLU -> 16-bit pack -> NHWC global store
-//                   (optionally strided into a wider concat buffer / the 2x up-sampled grid), or
-//                   for the head: softmax -> x255 round-half-even -> first-max argmax -> write the
-//                   label if this tile owns the output pixel (stitch fused).
+//   warps 4..7    : epilogue.  tcgen05.ld -> bias -> ReLU -> 16-bit pack -> 128B-swizzled staging
+//                   tile in shared memory -> TMA store (cp.async.bulk.tensor) of full 128-byte
+//                   pixel rows into the NHWC destination (a channel slice of a concat buffer, or one
+//                   parity of the 2x up-sampled grid through a strided tensor map); the 2x2 max
+//                   pool of the same tile is reduced with two warp shuffles and stored the same way.
 // Pipelines are mbarrier based (full/empty per A stage, per B stage, per accumulator stage).
 #include "conv_tc.cuh"
-#include "stitch.cuh"
 #include "tc_common.cuh"
 
 namespace ecseg {
@@ -33,95 +38,105 @@ using namespace tc;
 
 constexpr int kThreads = 256;
 constexpr int kEpiWarp0 = 4;
+constexpr int kHaloPitch = 18;
+constexpr int kABytes = 18 * 18 * 128;             // bytes one halo load delivers
+constexpr int kAStride = 41 * 1024;                // stage footprint (1024-aligned for SWIZZLE_128B)
+constexpr int kOutStage = 128 * 128;               // staging tile: 128 pixels x 64 channels x 2 B
+constexpr int kPoolStage = 32 * 128;               // pooled staging tile: 32 pixels x 64 channels
+constexpr int kMaxBars = 32;
+constexpr int kMaxCout = 1024;
 
-template <int N_TILE, int PITCH>
-struct Cfg {
-  static constexpr int kAStages = 2;
-  static constexpr int kABytes = 18 * 18 * 128;                                  // bytes one halo load delivers
-  static constexpr int kAStride = ((18 * PITCH * 128 + 1023) / 1024) * 1024;     // stage footprint
-  static constexpr int kBBytes = N_TILE * 128;
-  static constexpr int kBStride = ((kBBytes + 1023) / 1024) * 1024;
-  static constexpr int kBStages = (PITCH == 18) ? 4 : 3;
-  static constexpr int kAccStages = (4 * N_TILE <= 512) ? 2 : 1;
-  static constexpr int kTmemColsRaw = kAccStages * 2 * N_TILE;
-  static constexpr int kTmemCols = kTmemColsRaw <= 32 ? 32 : kTmemColsRaw <= 64 ? 64 : kTmemColsRaw <= 128 ? 128
-                                   : kTmemColsRaw <= 256 ? 256 : 512;
-  static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 2 * kAccStages;
-  static constexpr int kSmemBytes = kAStages * kAStride + kBStages * kBStride + kNumBars * 8 + 16 + 1024;
-};
+__host__ __device__ constexpr int smem_bytes(int n_tile, int a_stages, int b_stages) {
+  return a_stages * kAStride + b_stages * n_tile * 128 + 2 * kOutStage + 2 * kPoolStage + kMaxCout * 4 +
+         kMaxBars * 8 + 16 + 1024;
+}
 
-template <int N_TILE, int PITCH>
+template <int N_TILE, int NACC, int CS>
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__ ConvTcParams p) {
-  using C = Cfg<N_TILE, PITCH>;
+  constexpr int kBBytes = N_TILE * 128;
+  constexpr int kAccCols = 2 * NACC * N_TILE;
+  constexpr int kAccStages = (2 * kAccCols <= 512) ? 2 : 1;
+  constexpr int kTmemCols = 512;
+  static_assert(kAccCols <= 512, "accumulators exceed TMEM");
+
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B atoms repeat every 1024 B: align the stage area
+  // SWIZZLE_128B atoms repeat every 1024 B: align the stage area (same offset in every CTA of a cluster)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int AS = p.a_stages, BS = p.b_stages;
   const uint32_t a_base = smem_u32(smem);
-  const uint32_t b_base = a_base + C::kAStages * C::kAStride;
-  const uint32_t bar_base = b_base + C::kBStages * C::kBStride;
+  const uint32_t b_base = a_base + AS * kAStride;
+  const uint32_t o_base = b_base + BS * kBBytes;                 // 2 output staging tiles
+  const uint32_t q_base = o_base + 2 * kOutStage;                // 2 pooled staging tiles
+  float* s_bias = reinterpret_cast<float*>(smem + AS * kAStride + BS * kBBytes + 2 * kOutStage + 2 * kPoolStage);
+  const uint32_t bar_base = q_base + 2 * kPoolStage + kMaxCout * 4;
   auto full_a = [&](int s) { return bar_base + 8u * s; };
-  auto empty_a = [&](int s) { return bar_base + 8u * (C::kAStages + s); };
-  auto full_b = [&](int s) { return bar_base + 8u * (2 * C::kAStages + s); };
-  auto empty_b = [&](int s) { return bar_base + 8u * (2 * C::kAStages + C::kBStages + s); };
-  auto tmem_full = [&](int s) { return bar_base + 8u * (2 * C::kAStages + 2 * C::kBStages + s); };
-  auto tmem_empty = [&](int s) { return bar_base + 8u * (2 * C::kAStages + 2 * C::kBStages + C::kAccStages + s); };
-  uint32_t* tmem_ptr_smem =
-      reinterpret_cast<uint32_t*>(smem + C::kAStages * C::kAStride + C::kBStages * C::kBStride + C::kNumBars * 8);
+  auto empty_a = [&](int s) { return bar_base + 8u * (AS + s); };
+  auto full_b = [&](int s) { return bar_base + 8u * (2 * AS + s); };
+  auto empty_b = [&](int s) { return bar_base + 8u * (2 * AS + BS + s); };
+  auto tmem_full = [&](int s) { return bar_base + 8u * (2 * AS + 2 * BS + s); };
+  auto tmem_empty = [&](int s) { return bar_base + 8u * (2 * AS + 2 * BS + 2 + s); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + AS * kAStride + BS * kBBytes + 2 * kOutStage +
+                                                        2 * kPoolStage + kMaxCout * 4 + kMaxBars * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CS > 1 ? cluster_ctarank() : 0u;
+  const int cluster_id = blockIdx.x / CS, n_clusters = gridDim.x / CS;
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < C::kAStages; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
-    for (int s = 0; s < C::kBStages; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
-    for (int s = 0; s < C::kAccStages; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), 128); }
+    for (int s = 0; s < AS; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
+    for (int s = 0; s < BS; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), CS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                 "r"((uint32_t)C::kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tmem_alloc(smem_u32(tmem_ptr_smem), kTmemCols);
   } else if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tm_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tm_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tm_out[0]) : "memory");
+  }
+  {
+    const int cout = p.n_chunks * N_TILE;
+    for (int i = threadIdx.x; i < cout; i += kThreads) s_bias[i] = p.bias ? p.bias[i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();     // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
 
   const int bw = p.W >> 4, bh = p.H >> 4;
   const int n_mblocks = p.n_img * bh * bw;
-  const int n_work = n_mblocks * p.n_par * p.n_chunks;
+  const int n_mgroups = (n_mblocks + CS - 1) / CS;
+  const int n_items = n_mgroups * p.n_chunks;
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     int sa = 0, pa = 0, sb = 0, pb = 0;
     bool ok = true;
-    for (int wk = blockIdx.x; wk < n_work && ok; wk += gridDim.x) {
-      const int mb = wk % n_mblocks, rest = wk / n_mblocks;
-      const int par = rest % p.n_par, nch = rest / p.n_par;
+    for (int it = cluster_id; it < n_items && ok; it += n_clusters) {
+      const int mg = it % n_mgroups, nch = it / n_mgroups;
+      int mb = mg * CS + (int)rank;
+      if (mb >= n_mblocks) mb = n_mblocks - 1;    // ghost CTA of an odd tail: same loads, no stores
       const int img = mb / (bh * bw), rem = mb % (bh * bw);
       const int y0 = (rem / bw) << 4, x0 = (rem % bw) << 4;
-      const int ntaps = p.n_taps[par];
       for (int ch = 0; ch < p.cin_chunks && ok; ++ch) {
         ok = mbar_wait(empty_a(sa), pa ^ 1, p.device_error, 1);
         if (!ok) break;
-        mbar_expect_tx(full_a(sa), C::kABytes);
-        const uint32_t dst = a_base + sa * C::kAStride;
-        if (PITCH == 18) {
-          tma_load_4d(dst, &p.tm_a, full_a(sa), ch * 64, x0 - 1, y0 - 1, img);
-        } else {
-          for (int r = 0; r < 18; ++r)
-            tma_load_4d(dst + r * PITCH * 128, &p.tm_a, full_a(sa), ch * 64, x0 - 1, y0 - 1 + r, img);
-        }
-        if (++sa == C::kAStages) { sa = 0; pa ^= 1; }
-        for (int t = 0; t < ntaps; ++t) {
+        mbar_expect_tx(full_a(sa), kABytes);
+        tma_load_4d(a_base + sa * kAStride, &p.tm_a, full_a(sa), ch * 64, x0 - 1, y0 - 1, img);
+        if (++sa == AS) { sa = 0; pa ^= 1; }
+        for (int t = 0; t < 9; ++t) {
           ok = mbar_wait(empty_b(sb), pb ^ 1, p.device_error, 2);
           if (!ok) break;
-          mbar_expect_tx(full_b(sb), C::kBBytes);
-          tma_load_2d(b_base + sb * C::kBStride, &p.tm_b, full_b(sb), ch * 64,
-                      (int)p.tap_w[par][t] * p.cout_rows + nch * N_TILE);
-          if (++sb == C::kBStages) { sb = 0; pb ^= 1; }
+          mbar_expect_tx(full_b(sb), kBBytes);
+          const int row = t * p.cout_rows + nch * N_TILE;
+          if (CS == 1) {
+            tma_load_2d(b_base + sb * kBBytes, &p.tm_b, full_b(sb), ch * 64, row);
+          } else {
+            tma_load_2d_mc(b_base + sb * kBBytes + rank * (kBBytes / CS), &p.tm_b, full_b(sb), ch * 64,
+                           row + (int)rank * (N_TILE / CS), (uint16_t)((1u << CS) - 1));
+          }
+          if (++sb == BS) { sb = 0; pb ^= 1; }
         }
       }
     }
@@ -130,166 +145,210 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     const uint32_t idesc = make_idesc(128, N_TILE, p.is_bf16);
     int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
     bool ok = true;
-    for (int wk = blockIdx.x; wk < n_work && ok; wk += gridDim.x) {
-      const int par = (wk / n_mblocks) % p.n_par;
-      const int ntaps = p.n_taps[par];
+    for (int it = cluster_id; it < n_items && ok; it += n_clusters) {
       ok = mbar_wait(tmem_empty(as), pacc ^ 1, p.device_error, 3);
       if (!ok) break;
       tc_fence_after();
-      const uint32_t d0 = tmem_base + (uint32_t)(as * 2 * N_TILE);
-      uint32_t accumulate = 0;
+      const uint32_t d0 = tmem_base + (uint32_t)(as * kAccCols);
+      uint32_t started = 0;
       for (int ch = 0; ch < p.cin_chunks && ok; ++ch) {
         ok = mbar_wait(full_a(sa), pa, p.device_error, 4);
         if (!ok) break;
-        const uint32_t a_stage = a_base + sa * C::kAStride;
-        for (int t = 0; t < ntaps; ++t) {
+        const uint32_t a_stage = a_base + sa * kAStride;
+        for (int t = 0; t < 9; ++t) {
           ok = mbar_wait(full_b(sb), pb, p.device_error, 5);
           if (!ok) break;
           tc_fence_after();
-          const uint32_t b_stage = b_base + sb * C::kBStride;
-          const uint32_t a_view = a_stage + (uint32_t)(((int)p.tap_dy[par][t] * PITCH + (int)p.tap_dx[par][t]) * 128);
+          const uint32_t b_stage = b_base + sb * kBBytes;
+          const uint32_t a_view = a_stage + (uint32_t)(((int)p.tap_dy[t] * kHaloPitch + (int)p.tap_dx[t]) * 128);
+          const int acc = NACC > 1 ? (int)p.tap_acc[t] : 0;
+          const uint32_t d = d0 + (uint32_t)(acc * 2 * N_TILE);
+          uint32_t accumulate = (started >> acc) & 1u;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t bdesc = make_sdesc(b_stage + k * 32, 1024, 0);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-              const uint32_t a_addr = a_view + half * 8 * 128;
-              const uint32_t bo = p.desc_mode ? ((a_addr >> 7) & 7u) : 0u;
-              const uint64_t adesc = make_sdesc(a_addr + k * 32, PITCH * 128, bo);
-              umma_f16(d0 + half * N_TILE, adesc, bdesc, idesc, accumulate);
+              const uint64_t adesc = make_sdesc(a_view + half * 8 * 128 + k * 32, kHaloPitch * 128, 0);
+              umma_f16(d + half * N_TILE, adesc, bdesc, idesc, accumulate);
             }
             accumulate = 1;
           }
-          umma_commit(empty_b(sb));   // weight stage reusable once these MMAs retire
-          if (++sb == C::kBStages) { sb = 0; pb ^= 1; }
+          started |= 1u << acc;
+          // weight stage reusable (in every CTA of the cluster) once these MMAs retire
+          if (CS == 1) umma_commit(empty_b(sb));
+          else umma_commit_mc(empty_b(sb), (uint16_t)((1u << CS) - 1));
+          if (++sb == BS) { sb = 0; pb ^= 1; }
         }
         umma_commit(empty_a(sa));     // halo stage reusable
-        if (++sa == C::kAStages) { sa = 0; pa ^= 1; }
+        if (++sa == AS) { sa = 0; pa ^= 1; }
       }
-      umma_commit(tmem_full(as));     // accumulator complete -> epilogue
-      if (++as == C::kAccStages) { as = 0; pacc ^= 1; }
+      umma_commit(tmem_full(as));     // accumulators complete -> epilogue
+      if (++as == kAccStages) { as = 0; pacc ^= 1; }
     }
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int m = q * 32 + lane;            // accumulator row = pixel of the 16x8 half block
+    const int m = q * 32 + lane;            // accumulator row = pixel of the 16x8 half block = staging row
     const int r = m >> 3, c = m & 7;
+    const bool e0 = threadIdx.x == kEpiWarp0 * 32;
+    const bool pool_lane = (lane & 9) == 0;                 // even row, even column of the half block
+    const int pm = (r >> 1) * 4 + (c >> 1);                 // pooled staging row
     int as = 0, pacc = 0;
+    uint32_t sidx = 0;
     bool ok = true;
-    for (int wk = blockIdx.x; wk < n_work && ok; wk += gridDim.x) {
-      const int mb = wk % n_mblocks, rest = wk / n_mblocks;
-      const int par = rest % p.n_par, nch = rest / p.n_par;
+    for (int it = cluster_id; it < n_items && ok; it += n_clusters) {
+      const int mg = it % n_mgroups, nch = it / n_mgroups;
+      const int mb_raw = mg * CS + (int)rank;
+      const bool ghost = mb_raw >= n_mblocks;
+      const int mb = ghost ? n_mblocks - 1 : mb_raw;
       const int img = mb / (bh * bw), rem = mb % (bh * bw);
       const int y0 = (rem / bw) << 4, x0 = (rem % bw) << 4;
       ok = mbar_wait(tmem_full(as), pacc, p.device_error, 6);
       if (!ok) break;
       tc_fence_after();
-      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * N_TILE);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int y = y0 + r, x = x0 + half * 8 + c;
-        {
-          const int oy = y * p.oscale + p.par_oy[par], ox = x * p.oscale + p.par_ox[par];
-          uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) +
-                          (((size_t)img * p.out_H + oy) * p.out_W + ox) * p.out_pitch + p.out_choff + nch * N_TILE;
-          const float* bias = p.bias ? p.bias + nch * N_TILE : nullptr;
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccCols);
 #pragma unroll 1
-          for (int c0 = 0; c0 < N_TILE; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(t0 + half * N_TILE + c0, v);
-            tmem_ld_wait();
-            float f[16];
+      for (int acc = 0; acc < NACC; ++acc) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll 1
+          for (int sl = 0; sl < N_TILE / 64; ++sl) {
+            const uint32_t buf = sidx & 1u;
+            ++sidx;
+            if (e0) bulk_wait_read<1>();          // the store that last read this staging buffer is done
+            named_bar_sync(1, 128);
+            const uint32_t so = o_base + buf * kOutStage + (uint32_t)m * 128u;
+            const uint32_t sq = q_base + buf * kPoolStage + (uint32_t)pm * 128u;
+            const float* bs = s_bias + nch * N_TILE + sl * 64;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              f[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + c0 + j) : 0.f);
-              if (p.relu) f[j] = fmaxf(f[j], 0.f);
+            for (int cc = 0; cc < 2; ++cc) {
+              uint32_t v[32];
+              tmem_ld32(t0 + (uint32_t)((acc * 2 + half) * N_TILE + sl * 64 + cc * 32), v);
+              tmem_ld_wait();
+              float f[32];
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bs + cc * 32 + j);
+                f[j] = __uint_as_float(v[j]) + b4.x;         f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+                f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint4 o;
+                o.x = pack2(f[8 * k], f[8 * k + 1], p.is_bf16);     o.y = pack2(f[8 * k + 2], f[8 * k + 3], p.is_bf16);
+                o.z = pack2(f[8 * k + 4], f[8 * k + 5], p.is_bf16); o.w = pack2(f[8 * k + 6], f[8 * k + 7], p.is_bf16);
+                st_shared_v4(so + (uint32_t)(((cc * 4 + k) ^ c) << 4), o);
+              }
+              if (NACC == 1 && p.has_pool) {
+                // fused 2x2/2 max pool (models.py:28,40,52,64): the 2x2 window of pixel (r, c) lives in
+                // lanes ^1 (x neighbour) and ^8 (y neighbour); max commutes with the monotone rounding.
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
+                  f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 8));
+                }
+                if (pool_lane) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    uint4 o;
+                    o.x = pack2(f[8 * k], f[8 * k + 1], p.is_bf16);     o.y = pack2(f[8 * k + 2], f[8 * k + 3], p.is_bf16);
+                    o.z = pack2(f[8 * k + 4], f[8 * k + 5], p.is_bf16); o.w = pack2(f[8 * k + 6], f[8 * k + 7], p.is_bf16);
+                    st_shared_v4(sq + (uint32_t)(((cc * 4 + k) ^ (pm & 7)) << 4), o);
+                  }
+                }
+              }
             }
-            if (p.debug_dump && blockIdx.x == 0 && wk == blockIdx.x)
-              for (int j = 0; j < 16; ++j) p.debug_dump[(half * 128 + m) * N_TILE + c0 + j] = __uint_as_float(v[j]);
-            uint4 o0, o1;
-            o0.x = pack2(f[0], f[1], p.is_bf16);  o0.y = pack2(f[2], f[3], p.is_bf16);
-            o0.z = pack2(f[4], f[5], p.is_bf16);  o0.w = pack2(f[6], f[7], p.is_bf16);
-            o1.x = pack2(f[8], f[9], p.is_bf16);  o1.y = pack2(f[10], f[11], p.is_bf16);
-            o1.z = pack2(f[12], f[13], p.is_bf16); o1.w = pack2(f[14], f[15], p.is_bf16);
-            *reinterpret_cast<uint4*>(dst + c0) = o0;
-            *reinterpret_cast<uint4*>(dst + c0 + 8) = o1;
-            if (p.pool_out) {
-              // fused 2x2/2 max pool (models.py:28,40,52,64): the 2x2 window of pixel (r, c) lives in
-              // lanes ^1 (x neighbour) and ^8 (y neighbour); max commutes with the monotone rounding.
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
-                f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 8));
+            fence_async_smem();
+            named_bar_sync(2, 128);
+            if (e0) {
+              if (!ghost) {
+                const int ch0 = nch * N_TILE + sl * 64;
+                tma_store_4d(&p.tm_out[acc], o_base + buf * kOutStage, p.out_choff + ch0, x0 + half * 8, y0, img);
+                if (NACC == 1 && p.has_pool)
+                  tma_store_4d(&p.tm_pool, q_base + buf * kPoolStage, ch0, (x0 >> 1) + half * 4, y0 >> 1, img);
               }
-              if ((lane & 9) == 0) {
-                uint16_t* pd = reinterpret_cast<uint16_t*>(p.pool_out) +
-                               (((size_t)img * (p.out_H >> 1) + (y >> 1)) * (p.out_W >> 1) + (x >> 1)) * p.pool_pitch +
-                               nch * N_TILE + c0;
-                o0.x = pack2(f[0], f[1], p.is_bf16);  o0.y = pack2(f[2], f[3], p.is_bf16);
-                o0.z = pack2(f[4], f[5], p.is_bf16);  o0.w = pack2(f[6], f[7], p.is_bf16);
-                o1.x = pack2(f[8], f[9], p.is_bf16);  o1.y = pack2(f[10], f[11], p.is_bf16);
-                o1.z = pack2(f[12], f[13], p.is_bf16); o1.w = pack2(f[14], f[15], p.is_bf16);
-                *reinterpret_cast<uint4*>(pd) = o0;
-                *reinterpret_cast<uint4*>(pd + 8) = o1;
-              }
+              bulk_commit();
             }
           }
         }
       }
       tc_fence_before();
       mbar_arrive(tmem_empty(as));
-      if (++as == C::kAccStages) { as = 0; pacc ^= 1; }
+      if (++as == kAccStages) { as = 0; pacc ^= 1; }
     }
+    if (e0) bulk_wait<0>();
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();     // no CTA leaves while a peer may still multicast into it / signal it
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::kTmemCols)
-                 : "memory");
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
-template <int N_TILE, int PITCH>
-int launch_cfg(ecseg_ctx* ctx, const ConvTcParams& p, cudaStream_t st) {
-  using C = Cfg<N_TILE, PITCH>;
-  auto kern = k_conv_tc<N_TILE, PITCH>;
+template <int N_TILE, int NACC, int CS>
+int launch_cfg(ecseg_ctx* ctx, ConvTcParams& p, cudaStream_t st) {
+  auto kern = k_conv_tc<N_TILE, NACC, CS>;
+  // pipeline depths: halo stages first (each covers 9 taps of MMA work), the rest goes to weight stages
+  const int budget = 227 * 1024;
+  p.a_stages = (N_TILE == 64) ? 3 : 2;
+  p.b_stages = (budget - smem_bytes(N_TILE, p.a_stages, 0)) / (N_TILE * 128);
+  if (p.b_stages > 8) p.b_stages = 8;
+  if (p.b_stages < 2 || 2 * p.a_stages + 2 * p.b_stages + 4 > kMaxBars) { ctx->err = "conv_tc: bad pipeline configuration"; return ECSEG_E_INVALID; }
+  const int smem = smem_bytes(N_TILE, p.a_stages, p.b_stages);
   static bool attr_done = false;
   if (!attr_done) {
-    ECSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    ECSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
     attr_done = true;
   }
-  const int sms = ctx->n_sms;
-  const int n_work = p.n_img * (p.H >> 4) * (p.W >> 4) * p.n_par * p.n_chunks;
-  const int grid = n_work < sms ? n_work : sms;
-  kern<<<grid, kThreads, C::kSmemBytes, st>>>(p);
+  const int n_mblocks = p.n_img * (p.H >> 4) * (p.W >> 4);
+  const int n_items = ((n_mblocks + CS - 1) / CS) * p.n_chunks;
+  int clusters = ctx->n_sms / CS;
+  if (n_items < clusters) clusters = n_items;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(clusters * CS);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CS > 1 ? 1 : 0;
+  ECSEG_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   ECSEG_CHECK_LAUNCH();
   return ECSEG_OK;
 }
 
+template <int NACC, int CS>
+int launch_n(ecseg_ctx* ctx, ConvTcParams& p, int n_tile, cudaStream_t st) {
+  switch (n_tile) {
+    case 64: return launch_cfg<64, NACC, CS>(ctx, p, st);
+    case 128: if (NACC == 1) return launch_cfg<128, 1, CS>(ctx, p, st); break;
+    case 256: if (NACC == 1) return launch_cfg<256, 1, CS>(ctx, p, st); break;
+  }
+  ctx->err = "conv_tc: unsupported N_TILE for this layer kind";
+  return ECSEG_E_INVALID;
+}
+
 }  // namespace
 
-int conv_tc_launch(ecseg_ctx* ctx, const ConvTcParams& p, int n_tile, int pitch, cudaStream_t st) {
-  if ((p.H & 15) || (p.W & 15) || p.cin_chunks < 1 || p.n_chunks < 1) {
-    ctx->err = "conv_tc: H, W must be multiples of 16 and Cin a multiple of 64";
+int conv_tc_launch(ecseg_ctx* ctx, ConvTcParams& p, int n_tile, int cluster, cudaStream_t st) {
+  if ((p.H & 15) || (p.W & 15) || p.cin_chunks < 1 || p.n_chunks < 1 || p.n_chunks * n_tile > kMaxCout) {
+    ctx->err = "conv_tc: H, W must be multiples of 16, Cin a multiple of 64, Cout <= 1024";
     return ECSEG_E_INVALID;
   }
-  if (p.pool_out && p.oscale != 1) { ctx->err = "conv_tc: pool fusion needs a plain convolution"; return ECSEG_E_INVALID; }
-  if (pitch == 18) {
-    switch (n_tile) {
-      case 64: return launch_cfg<64, 18>(ctx, p, st);
-      case 128: return launch_cfg<128, 18>(ctx, p, st);
-      case 256: return launch_cfg<256, 18>(ctx, p, st);
-    }
-  } else if (pitch == 24) {
-    switch (n_tile) {
-      case 64: return launch_cfg<64, 24>(ctx, p, st);
-      case 128: return launch_cfg<128, 24>(ctx, p, st);
-      case 256: return launch_cfg<256, 24>(ctx, p, st);
-    }
-  }
-  ctx->err = "conv_tc: unsupported N_TILE / PITCH";
+  if (p.n_acc == 1) return cluster == 2 ? launch_n<1, 2>(ctx, p, n_tile, st) : launch_n<1, 1>(ctx, p, n_tile, st);
+  if (p.n_acc == 4) return cluster == 2 ? launch_n<4, 2>(ctx, p, n_tile, st) : launch_n<4, 1>(ctx, p, n_tile, st);
+  ctx->err = "conv_tc: n_acc must be 1 or 4";
   return ECSEG_E_INVALID;
 }
 
@@ -314,13 +373,13 @@ static PFN_encodeTiled get_encode(ecseg_ctx* ctx) {
   return fn;
 }
 
-int make_tm_act(ecseg_ctx* ctx, CUtensorMap* tm, const void* base, int C, int pitchC, int W, int H, int N, int box_h,
-                bool bf16) {
+int make_tm_nhwc(ecseg_ctx* ctx, CUtensorMap* tm, const void* base, int C, int W, int H, int N, size_t stride_w,
+                 size_t stride_h, size_t stride_n, int box_w, int box_h, bool bf16) {
   PFN_encodeTiled enc = get_encode(ctx);
   if (!enc) return ECSEG_E_CUDA;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)pitchC * 2, (cuuint64_t)W * pitchC * 2, (cuuint64_t)H * W * pitchC * 2};
-  cuuint32_t box[4] = {64, 18, (cuuint32_t)box_h, 1};
+  cuuint64_t strides[3] = {(cuuint64_t)stride_w * 2, (cuuint64_t)stride_h * 2, (cuuint64_t)stride_n * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -61,8 +61,8 @@ struct UNet {
   float* b[23] = {};     // folded bias [cout] (nullptr for the head)
   int cout_rows[23] = {};
   float* debug_dump = nullptr;
-  // tcgen05 knobs (ECSEG_TC_PITCH / ECSEG_TC_DESC_MODE / ECSEG_TC_NTILE_MAX env overrides)
-  int tc_pitch = 18, tc_desc_mode = 0, tc_ntile_max = 256;
+  // tcgen05 knobs (ECSEG_TC_CLUSTER / ECSEG_TC_NTILE_MAX env overrides)
+  int tc_cluster = 2, tc_ntile_max = 256;
   int stop_after = -1;   // debug: stop the forward after this layer
 };
 
@@ -105,16 +105,17 @@ __device__ __forceinline__ void store8(__nv_bfloat16* dst, const float v[8]) {
   *reinterpret_cast<uint4*>(dst) = o;
 }
 
+constexpr int kFirstRows = 16;   // rows of one column a thread walks down
+
+// Block = 32 columns x 8 channel groups; a thread keeps the 9x8 weights of its channel group in
+// registers and slides a 3x3 window down `kFirstRows` rows of its column (3 new bytes per pixel),
+// so the kernel is bound by its 128 B/pixel output stream.  A warp writes 4 pixels x 128 B
+// contiguous per store.
 template <typename T>
 __global__ void __launch_bounds__(256) k_conv_first(const uint8_t* __restrict__ tiles, const uint8_t* __restrict__ pre,
                                                     TileGrid g, const float* __restrict__ w9x64,
                                                     const float* __restrict__ bias, T* __restrict__ out) {
-  __shared__ float sw[9 * 64];
-  __shared__ float sb[64];
-  for (int i = threadIdx.x; i < 9 * 64; i += 256) sw[i] = w9x64[i];
-  if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
-  const int img = blockIdx.z, y = blockIdx.y;
+  const int img = blockIdx.z, y0 = blockIdx.y * kFirstRows;
   const int x = blockIdx.x * 32 + (threadIdx.x >> 3);
   const int cg = (threadIdx.x & 7) * 8;
   const uint8_t* src;
@@ -125,26 +126,47 @@ __global__ void __launch_bounds__(256) k_conv_first(const uint8_t* __restrict__ 
     src = pre + (size_t)g.start_r(ri) * g.w + g.start_c(ci);
     pitch = g.w;
   }
-  float acc[8];
+  float w[9][8], b[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = sb[cg + j];
-#pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-    const int yy = y + ky - 1;
-    if (yy < 0 || yy >= kTile) continue;   // 'same' padding at the TILE border (tile-wise semantics)
-#pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int xx = x + kx - 1;
-      if (xx < 0 || xx >= kTile) continue;
-      const float v = (float)src[(size_t)yy * pitch + xx];
-      const float* wp = sw + (ky * 3 + kx) * 64 + cg;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wp[j], acc[j]);
-    }
+  for (int t = 0; t < 9; ++t) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w9x64 + t * 64 + cg));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w9x64 + t * 64 + cg + 4));
+    w[t][0] = w0.x; w[t][1] = w0.y; w[t][2] = w0.z; w[t][3] = w0.w;
+    w[t][4] = w1.x; w[t][5] = w1.y; w[t][6] = w1.z; w[t][7] = w1.w;
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
-  store8(out + (((size_t)img * kTile + y) * kTile + x) * 64 + cg, acc);
+  for (int j = 0; j < 8; ++j) b[j] = __ldg(bias + cg + j);
+  // 'same' padding at the TILE border (tile-wise semantics): out-of-tile taps read as 0
+  auto row = [&](int yy, float v[3]) {
+    const bool in = yy >= 0 && yy < kTile;
+    const uint8_t* r = src + (size_t)(in ? yy : 0) * pitch + x;
+    v[0] = (in && x > 0) ? (float)r[-1] : 0.f;
+    v[1] = in ? (float)r[0] : 0.f;
+    v[2] = (in && x < kTile - 1) ? (float)r[1] : 0.f;
+  };
+  float win[3][3];
+  row(y0 - 1, win[0]);
+  row(y0, win[1]);
+  T* dst = out + (((size_t)img * kTile + y0) * kTile + x) * 64 + cg;
+#pragma unroll 4
+  for (int dy = 0; dy < kFirstRows; ++dy) {
+    row(y0 + dy + 1, win[2]);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = b[j];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(win[ky][kx], w[ky * 3 + kx][j], acc[j]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    store8(dst, acc);
+    dst += (size_t)kTile * 64;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) { win[0][kx] = win[1][kx]; win[1][kx] = win[2][kx]; }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -319,8 +341,7 @@ static void fill_taps(P& p, bool convT) {
 // ------------------------------------------------------------------------------------------------
 int unet_create(ecseg_ctx* ctx) {
   ctx->net = new UNet();
-  if (const char* e = getenv("ECSEG_TC_PITCH")) ctx->net->tc_pitch = atoi(e);
-  if (const char* e = getenv("ECSEG_TC_DESC_MODE")) ctx->net->tc_desc_mode = atoi(e);
+  if (const char* e = getenv("ECSEG_TC_CLUSTER")) ctx->net->tc_cluster = atoi(e) == 1 ? 1 : 2;
   if (const char* e = getenv("ECSEG_TC_NTILE_MAX")) ctx->net->tc_ntile_max = atoi(e);
   return ECSEG_OK;
 }
@@ -441,7 +462,7 @@ static int run_first(ecseg_ctx* ctx, const uint8_t* d_tiles, const uint8_t* d_pr
                      cudaStream_t st) {
   UNet* net = ctx->net;
   TileGrid g = grid ? *grid : TileGrid{};
-  k_conv_first<T><<<dim3(kTile / 32, kTile, n), 256, 0, st>>>(d_tiles, d_pre, g, (const float*)net->w[0], net->b[0],
+  k_conv_first<T><<<dim3(kTile / 32, kTile / kFirstRows, n), 256, 0, st>>>(d_tiles, d_pre, g, (const float*)net->w[0], net->b[0],
                                                             (T*)net->buf[A0]);
   ECSEG_CHECK_LAUNCH();
   return ECSEG_OK;
@@ -492,10 +513,12 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   const LayerDef& l = kLayers[li];
   const Wire& wr = kWires[li];
   const bool bf16 = net->precision == ECSEG_PREC_BF16;
+  const int NT = ctx->max_tiles;
   if (li == 22) {
     HeadTcParams h;
     memset(&h, 0, sizeof(h));
-    ECSEG_TRY(make_tm_act(ctx, &h.tm_a, net->buf[wr.in], l.cin, kBufs[wr.in].ch, kTile, kTile, ctx->max_tiles, 18, bf16));
+    const size_t pc = kBufs[wr.in].ch;
+    ECSEG_TRY(make_tm_nhwc(ctx, &h.tm_a, net->buf[wr.in], l.cin, kTile, kTile, NT, pc, pc * kTile, pc * kTile * kTile, 18, 18, bf16));
     ECSEG_TRY(make_tm_wgt(ctx, &h.tm_b, net->w[li], l.cin, 48, 48, bf16));
     h.n_img = n; h.is_bf16 = bf16;
     h.probs = d_probs; h.logits = d_logits; h.labels = d_labels;
@@ -505,25 +528,51 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   }
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
-  fill_taps(p, l.convT != 0);
   const int out_hw = kTile >> l.level;
   const int in_hw = l.convT ? out_hw / 2 : out_hw;
   const int rows = net->cout_rows[li];
-  int n_tile = rows < net->tc_ntile_max ? rows : net->tc_ntile_max;
+  int n_tile = l.convT ? 64 : (rows < net->tc_ntile_max ? rows : net->tc_ntile_max);
   if (n_tile > 256) n_tile = 256;
-  ECSEG_TRY(make_tm_act(ctx, &p.tm_a, net->buf[wr.in], l.cin, kBufs[wr.in].ch, in_hw, in_hw, ctx->max_tiles,
-                        net->tc_pitch == 18 ? 18 : 1, bf16));
-  ECSEG_TRY(make_tm_wgt(ctx, &p.tm_b, net->w[li], l.cin, 9 * rows, n_tile, bf16));
+  const int cs = net->tc_cluster;
+  const size_t pin = kBufs[wr.in].ch, pout = kBufs[wr.out].ch;
+  ECSEG_TRY(make_tm_nhwc(ctx, &p.tm_a, net->buf[wr.in], l.cin, in_hw, in_hw, NT, pin, pin * in_hw, pin * in_hw * in_hw, 18, 18, bf16));
+  ECSEG_TRY(make_tm_wgt(ctx, &p.tm_b, net->w[li], l.cin, 9 * rows, n_tile / cs, bf16));
+  const size_t esz = 2;
+  if (!l.convT) {
+    p.n_acc = 1;
+    for (int t = 0; t < 9; ++t) { p.tap_dy[t] = (signed char)(t / 3); p.tap_dx[t] = (signed char)(t % 3); p.tap_acc[t] = 0; }
+    ECSEG_TRY(make_tm_nhwc(ctx, &p.tm_out[0], net->buf[wr.out], (int)pout, out_hw, out_hw, NT, pout, pout * out_hw,
+                           pout * out_hw * out_hw, 8, 16, bf16));
+    if (wr.pool_to >= 0) {   // fused 2x2 max pool
+      const size_t pp = kBufs[wr.pool_to].ch;
+      const int ph = out_hw / 2;
+      ECSEG_TRY(make_tm_nhwc(ctx, &p.tm_pool, net->buf[wr.pool_to], (int)pp, ph, ph, NT, pp, pp * ph, pp * ph * ph, 4, 8, bf16));
+      p.has_pool = 1;
+    }
+  } else {
+    // TF 'same' stride-2 transposed conv: out[2i+ky, 2j+kx] += in[i,j] * K[ky,kx], cropped to 2H x 2W.
+    // Output parity (py,px): ky in {0,2} for py == 0 (input rows i and i-1), ky == 1 for py == 1.
+    p.n_acc = 4;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        const int t = ky * 3 + kx;
+        p.tap_dy[t] = (signed char)(ky == 2 ? 0 : 1);   // halo row of input (i-1) is 0, of i is 1
+        p.tap_dx[t] = (signed char)(kx == 2 ? 0 : 1);
+        p.tap_acc[t] = (signed char)((ky == 1 ? 2 : 0) + (kx == 1 ? 1 : 0));
+      }
+    for (int par = 0; par < 4; ++par) {   // one strided view of the 2x grid per output parity
+      const int py = par >> 1, px = par & 1;
+      const char* base = (const char*)net->buf[wr.out] + ((size_t)py * out_hw + px) * pout * esz;
+      ECSEG_TRY(make_tm_nhwc(ctx, &p.tm_out[par], base, (int)pout, in_hw, in_hw, NT, 2 * pout, 2 * pout * out_hw,
+                             pout * out_hw * out_hw, 8, 16, bf16));
+    }
+  }
   p.H = in_hw; p.W = in_hw; p.n_img = n;
   p.cin_chunks = l.cin / 64; p.n_chunks = rows / n_tile; p.cout_rows = rows;
+  p.out_choff = wr.choff;
   p.bias = net->b[li]; p.relu = l.relu; p.is_bf16 = bf16;
-  p.desc_mode = net->tc_desc_mode;
   p.device_error = &ctx->counters->device_error;
-  p.debug_dump = nullptr;
-  p.out = net->buf[wr.out]; p.out_H = out_hw; p.out_W = out_hw;
-  p.out_pitch = kBufs[wr.out].ch; p.out_choff = wr.choff;
-  if (wr.pool_to >= 0) { p.pool_out = net->buf[wr.pool_to]; p.pool_pitch = kBufs[wr.pool_to].ch; }   // fused max pool
-  return conv_tc_launch(ctx, p, n_tile, net->tc_pitch, st);
+  return conv_tc_launch(ctx, p, n_tile, cs, st);
 }
 
 int unet_forward(ecseg_ctx* ctx, const uint8_t* d_tiles, const uint8_t* d_pre, const TileGrid* grid, int n,
@@ -573,12 +622,11 @@ int unet_debug_layer(ecseg_ctx* ctx, int layer, int n, float* d_out, cudaStream_
   return ECSEG_OK;
 }
 
-int unet_set_debug(ecseg_ctx* ctx, int stop_after, int tc_pitch, int tc_desc_mode, int tc_ntile_max) {
+int unet_set_debug(ecseg_ctx* ctx, int stop_after, int tc_cluster, int tc_ntile_max) {
   UNet* net = ctx->net;
   if (!net) return ECSEG_E_STATE;
   net->stop_after = stop_after;
-  if (tc_pitch == 18 || tc_pitch == 24) net->tc_pitch = tc_pitch;
-  if (tc_desc_mode == 0 || tc_desc_mode == 1) net->tc_desc_mode = tc_desc_mode;
+  if (tc_cluster == 1 || tc_cluster == 2) net->tc_cluster = tc_cluster;
   if (tc_ntile_max == 64 || tc_ntile_max == 128 || tc_ntile_max == 256) net->tc_ntile_max = tc_ntile_max;
   return ECSEG_OK;
 }

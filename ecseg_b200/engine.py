@@ -85,8 +85,8 @@ class Engine:
                                               PRECISIONS[precision]))
         self.precision = precision
 
-    def debug_set(self, stop_after=-1, tc_pitch=0, tc_desc_mode=-1, tc_ntile_max=0):
-        self._chk(self.lib.ecseg_debug_set(self.ctx, stop_after, tc_pitch, tc_desc_mode, tc_ntile_max))
+    def debug_set(self, stop_after=-1, tc_cluster=0, tc_ntile_max=0):
+        self._chk(self.lib.ecseg_debug_set(self.ctx, stop_after, tc_cluster, tc_ntile_max))
 
     def device_error(self) -> int:
         code = c_int()

@@ -16,6 +16,7 @@ import numpy as np
 import yaml
 
 from . import spec
+from .shard import write_csv
 from .utils import count_cc, get_imgs, load_model, meta_segment  # noqa: F401
 
 MODEL_NAME = 'metaseg.h5'
@@ -62,11 +63,7 @@ def main(argv):
         raise NameError("name 'path_split' is not defined")
     csv_path = os.path.join(path_split[0], 'ec_quantification.csv')
     print("Saving ec quantification to", csv_path)
-    with open(csv_path, 'w') as f:
-        f.write('image name,# of ec\n')
-        for name, n in rows:
-            name = '"' + name.replace('"', '""') + '"' if (',' in name or '"' in name) else name
-            f.write(f'{name},{n}\n')
+    write_csv(csv_path, rows)
 
 
 if __name__ == "__main__":

@@ -131,9 +131,9 @@ int ecseg_segment_image_host(ecseg_ctx* ctx, const void* h_img, int h, int w, in
 int ecseg_debug_layer_output(ecseg_ctx* ctx, int layer, int n, float* d_out, void* stream);
 
 /* Debug knobs: stop the U-Net forward after `stop_after_layer` (-1 = run everything) and select the
- * tcgen05 kernel variant (halo pitch 18|24, descriptor base-offset mode 0|1, max N tile 64|128|256);
+ * tcgen05 kernel variant (cluster size 1|2 = weight-tile multicast off|on, max N tile 64|128|256);
  * values outside those sets leave the setting unchanged. */
-int ecseg_debug_set(ecseg_ctx* ctx, int stop_after_layer, int tc_pitch, int tc_desc_mode, int tc_ntile_max);
+int ecseg_debug_set(ecseg_ctx* ctx, int stop_after_layer, int tc_cluster, int tc_ntile_max);
 
 /* Synchronise and read the device-side pipeline watchdog flag (0 = healthy). */
 int ecseg_device_error(ecseg_ctx* ctx, int* code);

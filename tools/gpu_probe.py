@@ -96,28 +96,15 @@ def main():
     mx, mean, scale = err_stats(logits.cpu().numpy(), z_ref)
     say(f"fp32 logits max_rel={mx:.3e} mean_rel={mean:.3e} scale={scale:.3g}")
 
-    # ---- tcgen05 variants, first tensor-core layer only ----
-    good = None
-    for prec in ("fp16",):
+    # ---- tcgen05 variants: cluster size (weight multicast) x max N tile ----
+    variants = [("fp16", 1, 256), ("fp16", 2, 256), ("fp16", 2, 128), ("fp16", 2, 64), ("bf16", 2, 256)]
+    if os.environ.get("PROBE_QUICK"):
+        variants = [("fp16", 1, 256), ("fp16", 2, 256)]
+    for prec, cs, ntile in variants:
         eng.load_weights(w, prec)
-        for pitch in (18, 24):
-            for mode in (0, 1):
-                eng.debug_set(tc_pitch=pitch, tc_desc_mode=mode)
-                tag = f"{prec} pitch={pitch} desc_mode={mode}"
-                rows = run_layers(tag, upto=1, verbose_layer=1)
-                ok = rows[-1][1] is not None and rows[-1][1] < 2e-2
-                say(tag, "->", "OK" if ok else "WRONG")
-                if ok and good is None:
-                    good = (pitch, mode)
-    say("first working tcgen05 variant:", good)
-    if good is None:
-        say("no tcgen05 variant reproduces conv1-2; stopping")
-        return 1
-    for prec in ("fp16", "bf16"):
-        eng.load_weights(w, prec)
-        for ntile in (256, 128):
-            eng.debug_set(tc_pitch=good[0], tc_desc_mode=good[1], tc_ntile_max=ntile)
-            results[f"{prec}/{ntile}"] = run_layers(f"{prec} ntile_max={ntile}")
+        if True:
+            eng.debug_set(tc_cluster=cs, tc_ntile_max=ntile)
+            results[f"{prec}/cs{cs}/{ntile}"] = run_layers(f"{prec} cluster={cs} ntile_max={ntile}")
             probs, logits = eng.unet_forward(tiles[..., 0], want_logits=True)
             torch.cuda.synchronize()
             mx, mean, scale = err_stats(logits.cpu().numpy(), z_ref)
@@ -128,7 +115,7 @@ def main():
             srt = np.sort(q_ref, -1)
             notie = srt[..., 3] != srt[..., 2]
             agree = float((lab_g == lab_r)[notie].mean())
-            say(f"{prec} ntile_max={ntile} logits max_rel={mx:.3e} mean_rel={mean:.3e}; label agreement excl. ties "
+            say(f"{prec} cluster={cs} ntile_max={ntile} logits max_rel={mx:.3e} mean_rel={mean:.3e}; label agreement excl. ties "
                 f"{agree * 100:.4f}% (ties {100 - notie.mean() * 100:.3f}%), dev_err={eng.device_error()}")
     json.dump({k: v for k, v in results.items()}, open(os.path.join(OUT, "probe.json"), "w"))
     return 0
