@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + AS * kAStride + BS * kBBytes + 2 * kOutStage +
                                                         2 * kPoolStage + kMaxCout * 4 + kMaxBars * 8);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const uint32_t rank = CS > 1 ? cluster_ctarank() : 0u;
   const int cluster_id = blockIdx.x / CS, n_clusters = gridDim.x / CS;
 
@@ -102,15 +102,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
   __syncthreads();
   if (CS > 1) cluster_sync_all();     // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem), 0);
 
   const int bw = p.W >> 4, bh = p.H >> 4;
   const int n_mblocks = p.n_img * bh * bw;
   const int n_mgroups = (n_mblocks + CS - 1) / CS;
   const int n_items = n_mgroups * p.n_chunks;
 
-  if (warp == 0 && lane == 0) {
+  // Producer and MMA roles run as WHOLE warps with warp-uniform control flow: every lane waits on the
+  // mbarriers, one elected lane issues.  That keeps descriptors / coordinates in uniform registers
+  // (UTCHMMA / UTMALDG take uniform-register operands); a role entered as `lane == 0` makes ptxas
+  // wrap every issue in a divergence "waterfall" that costs more than a small-N MMA itself.
+  if (warp == 0) {
     // ===================== TMA producer =====================
+    const bool leader = elect_one();
     int sa = 0, pa = 0, sb = 0, pb = 0;
     bool ok = true;
     for (int it = cluster_id; it < n_items && ok; it += n_clusters) {
@@ -120,70 +125,79 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
       const int img = mb / (bh * bw), rem = mb % (bh * bw);
       const int y0 = (rem / bw) << 4, x0 = (rem % bw) << 4;
       for (int ch = 0; ch < p.cin_chunks && ok; ++ch) {
-        ok = mbar_wait(empty_a(sa), pa ^ 1, p.device_error, 1);
+        ok = __all_sync(0xffffffffu, mbar_wait(empty_a(sa), pa ^ 1, p.device_error, 1));
         if (!ok) break;
-        mbar_expect_tx(full_a(sa), kABytes);
-        tma_load_4d(a_base + sa * kAStride, &p.tm_a, full_a(sa), ch * 64, x0 - 1, y0 - 1, img);
+        if (leader) {
+          mbar_expect_tx(full_a(sa), kABytes);
+          tma_load_4d(a_base + sa * kAStride, &p.tm_a, full_a(sa), ch * 64, x0 - 1, y0 - 1, img);
+        }
         if (++sa == AS) { sa = 0; pa ^= 1; }
         for (int t = 0; t < 9; ++t) {
-          ok = mbar_wait(empty_b(sb), pb ^ 1, p.device_error, 2);
+          ok = __all_sync(0xffffffffu, mbar_wait(empty_b(sb), pb ^ 1, p.device_error, 2));
           if (!ok) break;
-          mbar_expect_tx(full_b(sb), kBBytes);
-          const int row = t * p.cout_rows + nch * N_TILE;
-          if (CS == 1) {
-            tma_load_2d(b_base + sb * kBBytes, &p.tm_b, full_b(sb), ch * 64, row);
-          } else {
-            tma_load_2d_mc(b_base + sb * kBBytes + rank * (kBBytes / CS), &p.tm_b, full_b(sb), ch * 64,
-                           row + (int)rank * (N_TILE / CS), (uint16_t)((1u << CS) - 1));
+          if (leader) {
+            mbar_expect_tx(full_b(sb), kBBytes);
+            const int row = t * p.cout_rows + nch * N_TILE;
+            if (CS == 1) {
+              tma_load_2d(b_base + sb * kBBytes, &p.tm_b, full_b(sb), ch * 64, row);
+            } else {
+              tma_load_2d_mc(b_base + sb * kBBytes + rank * (kBBytes / CS), &p.tm_b, full_b(sb), ch * 64,
+                             row + (int)rank * (N_TILE / CS), (uint16_t)((1u << CS) - 1));
+            }
           }
           if (++sb == BS) { sb = 0; pb ^= 1; }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    const bool leader = elect_one();
     const uint32_t idesc = make_idesc(128, N_TILE, p.is_bf16);
+    const uint32_t a_hi = sdesc_hi(kHaloPitch * 128), b_hi = sdesc_hi(1024);
     int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
     bool ok = true;
     for (int it = cluster_id; it < n_items && ok; it += n_clusters) {
-      ok = mbar_wait(tmem_empty(as), pacc ^ 1, p.device_error, 3);
+      ok = __all_sync(0xffffffffu, mbar_wait(tmem_empty(as), pacc ^ 1, p.device_error, 3));
       if (!ok) break;
       tc_fence_after();
       const uint32_t d0 = tmem_base + (uint32_t)(as * kAccCols);
       uint32_t started = 0;
       for (int ch = 0; ch < p.cin_chunks && ok; ++ch) {
-        ok = mbar_wait(full_a(sa), pa, p.device_error, 4);
+        ok = __all_sync(0xffffffffu, mbar_wait(full_a(sa), pa, p.device_error, 4));
         if (!ok) break;
         const uint32_t a_stage = a_base + sa * kAStride;
+#pragma unroll
         for (int t = 0; t < 9; ++t) {
-          ok = mbar_wait(full_b(sb), pb, p.device_error, 5);
+          ok = __all_sync(0xffffffffu, mbar_wait(full_b(sb), pb, p.device_error, 5));
           if (!ok) break;
           tc_fence_after();
-          const uint32_t b_stage = b_base + sb * kBBytes;
-          const uint32_t a_view = a_stage + (uint32_t)(((int)p.tap_dy[t] * kHaloPitch + (int)p.tap_dx[t]) * 128);
+          const uint32_t b_lo = sdesc_lo(b_base + sb * kBBytes);
+          const uint32_t a_lo = sdesc_lo(a_stage + (uint32_t)(((int)p.tap_dy[t] * kHaloPitch + (int)p.tap_dx[t]) * 128));
           const int acc = NACC > 1 ? (int)p.tap_acc[t] : 0;
           const uint32_t d = d0 + (uint32_t)(acc * 2 * N_TILE);
-          uint32_t accumulate = (started >> acc) & 1u;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t bdesc = make_sdesc(b_stage + k * 32, 1024, 0);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const uint64_t adesc = make_sdesc(a_view + half * 8 * 128 + k * 32, kHaloPitch * 128, 0);
-              umma_f16(d + half * N_TILE, adesc, bdesc, idesc, accumulate);
-            }
-            accumulate = 1;
-          }
+          const uint32_t first = (started >> acc) & 1u;
           started |= 1u << acc;
-          // weight stage reusable (in every CTA of the cluster) once these MMAs retire
-          if (CS == 1) umma_commit(empty_b(sb));
-          else umma_commit_mc(empty_b(sb), (uint16_t)((1u << CS) - 1));
+          if (leader) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+              for (int half = 0; half < 2; ++half)
+                umma_f16(d + half * N_TILE, sdesc_join(a_lo + half * 64 + k * 2, a_hi), sdesc_join(b_lo + k * 2, b_hi),
+                         idesc, k > 0 ? 1u : first);
+            }
+            // weight stage reusable (in every CTA of the cluster) once these MMAs retire
+            if (CS == 1) umma_commit(empty_b(sb));
+            else umma_commit_mc(empty_b(sb), (uint16_t)((1u << CS) - 1));
+          }
+          __syncwarp();
           if (++sb == BS) { sb = 0; pb ^= 1; }
         }
-        umma_commit(empty_a(sa));     // halo stage reusable
+        if (leader) umma_commit(empty_a(sa));     // halo stage reusable
+        __syncwarp();
         if (++sa == AS) { sa = 0; pa ^= 1; }
       }
-      umma_commit(tmem_full(as));     // accumulators complete -> epilogue
+      if (leader) umma_commit(tmem_full(as));     // accumulators complete -> epilogue
+      __syncwarp();
       if (++as == kAccStages) { as = 0; pacc ^= 1; }
     }
   } else if (warp >= kEpiWarp0) {

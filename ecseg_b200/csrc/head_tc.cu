@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_head_tc(const __grid_constant__
   auto tmem_empty = [&](int s) { return bar_base + 8u * (2 * kAStages + 3 + s); };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kAStages * kAStride + kBStride + kZBytes + kNumBars * 8);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kAStages; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
@@ -71,48 +71,57 @@ __global__ void __launch_bounds__(kThreads, 1) k_head_tc(const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem), 0);
 
   constexpr int kBlocksPerImg = (kTile / 16) * (kTile / 16);
   const int n_work = p.n_img * kBlocksPerImg;
 
-  if (warp == 0 && lane == 0) {
+  // whole-warp roles with warp-uniform control flow, one elected lane issues (see conv_tc.cu)
+  if (warp == 0) {
     // ===================== TMA producer =====================
-    mbar_expect_tx(full_b, kBBytes);
-    tma_load_2d(b_base, &p.tm_b, full_b, 0, 0);
+    const bool leader = elect_one();
+    if (leader) {
+      mbar_expect_tx(full_b, kBBytes);
+      tma_load_2d(b_base, &p.tm_b, full_b, 0, 0);
+    }
     int sa = 0, pa = 0;
     for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
       const int img = wk / kBlocksPerImg, rem = wk % kBlocksPerImg;
       const int y0 = (rem / (kTile / 16)) << 4, x0 = (rem % (kTile / 16)) << 4;
-      if (!mbar_wait(empty_a(sa), pa ^ 1, p.device_error, 11)) break;
-      mbar_expect_tx(full_a(sa), kABytes);
-      tma_load_4d(a_base + sa * kAStride, &p.tm_a, full_a(sa), 0, x0 - 1, y0 - 1, img);
+      if (!__all_sync(0xffffffffu, mbar_wait(empty_a(sa), pa ^ 1, p.device_error, 11))) break;
+      if (leader) {
+        mbar_expect_tx(full_a(sa), kABytes);
+        tma_load_4d(a_base + sa * kAStride, &p.tm_a, full_a(sa), 0, x0 - 1, y0 - 1, img);
+      }
       if (++sa == kAStages) { sa = 0; pa ^= 1; }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    const bool leader = elect_one();
     const uint32_t idesc = make_idesc(128, kNRows, p.is_bf16);
+    const uint32_t hi = sdesc_hi(1024);
+    const uint32_t b_lo = sdesc_lo(b_base);
     int sa = 0, pa = 0, as = 0, pacc = 0;
-    bool ok = mbar_wait(full_b, 0, p.device_error, 12);
+    bool ok = __all_sync(0xffffffffu, mbar_wait(full_b, 0, p.device_error, 12));
     for (int wk = blockIdx.x; wk < n_work && ok; wk += gridDim.x) {
-      ok = mbar_wait(tmem_empty(as), pacc ^ 1, p.device_error, 13);
+      ok = __all_sync(0xffffffffu, mbar_wait(tmem_empty(as), pacc ^ 1, p.device_error, 13));
       if (!ok) break;
-      ok = mbar_wait(full_a(sa), pa, p.device_error, 14);
+      ok = __all_sync(0xffffffffu, mbar_wait(full_a(sa), pa, p.device_error, 14));
       if (!ok) break;
       tc_fence_after();
-      const uint32_t a_stage = a_base + sa * kAStride;
+      const uint32_t a_lo = sdesc_lo(a_base + sa * kAStride);
+      if (leader) {
 #pragma unroll
-      for (int mt = 0; mt < 3; ++mt) {
-        const uint32_t d = tmem_base + (uint32_t)(as * kAccCols + mt * 64);
+        for (int mt = 0; mt < 3; ++mt) {
+          const uint32_t d = tmem_base + (uint32_t)(as * kAccCols + mt * 64);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t adesc = make_sdesc(a_stage + mt * (128 * 128) + k * 32, 1024, 0);
-          const uint64_t bdesc = make_sdesc(b_base + k * 32, 1024, 0);
-          umma_f16(d, adesc, bdesc, idesc, k > 0);
+          for (int k = 0; k < 4; ++k)
+            umma_f16(d, sdesc_join(a_lo + mt * (128 * 128 / 16) + k * 2, hi), sdesc_join(b_lo + k * 2, hi), idesc, k > 0);
         }
+        umma_commit(empty_a(sa));
+        umma_commit(tmem_full(as));
       }
-      umma_commit(empty_a(sa));
-      umma_commit(tmem_full(as));
+      __syncwarp();
       if (++sa == kAStages) { sa = 0; pa ^= 1; }
       if (++as == 2) { as = 0; pacc ^= 1; }
     }

@@ -94,6 +94,23 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t sbo, uin
   return d;
 }
 
+
+// One lane of a fully converged warp (the same lane every time for a full mask).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// Warp index as a value ptxas knows to be warp-uniform (so that everything derived from it can live in
+// uniform registers: tcgen05.mma / TMA operands are uniform-register operands in SASS).
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
+// Descriptor words split so the per-MMA update is one 32-bit add: lo = start address field (+ canonical LBO),
+// hi = stride byte offset, version, swizzle.
+__device__ __forceinline__ uint32_t sdesc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint32_t sdesc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ uint64_t sdesc_join(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
 // Instruction descriptor, kind::f16: fp32 accumulate, A/B both K-major.
 __device__ __forceinline__ uint32_t make_idesc(int m, int n, int bf16) {
   uint32_t d = 0;
