@@ -35,6 +35,9 @@ SIGNATURES = {
                                     c_void_p, c_int, c_void_p]),
     "ecseg_segment_image_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                          POINTER(c_int32), POINTER(c_int64), c_int]),
+    "ecseg_segment_image_host_async": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                               c_int, c_void_p]),
+    "ecseg_segment_image_host_wait": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int64)]),
     "ecseg_debug_layer_output": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ecseg_debug_set": (c_int, [c_void_p, c_int, c_int, c_int]),
     "ecseg_device_error": (c_int, [c_void_p, POINTER(c_int)]),

@@ -53,6 +53,8 @@ int ecseg_ctx_create(ecseg_ctx** out, int device, int max_h, int max_w, int max_
   A((void**)&ctx->counters, sizeof(Counters));
   A((void**)&ctx->img_in, P * 8); A((void**)&ctx->pre, P); A((void**)&ctx->dapi, P); A((void**)&ctx->labels, P);
   A((void**)&ctx->d_n_ec, 8); A((void**)&ctx->d_ec_px, 8);
+  if (ok && cudaMallocHost((void**)&ctx->h_result, sizeof(*ctx->h_result)) != cudaSuccess) ok = false;
+  if (ok && cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming) != cudaSuccess) ok = false;
   if (ok && cudaMemset(ctx->counters, 0, sizeof(Counters)) != cudaSuccess) ok = false;
   for (auto& e : ctx->ev) if (ok && cudaEventCreate(&e) != cudaSuccess) ok = false;
   if (ok && unet_create(ctx) != ECSEG_OK) ok = false;
@@ -71,6 +73,8 @@ void ecseg_ctx_destroy(ecseg_ctx* ctx) {
                   ctx->d_n_ec, ctx->d_ec_px};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+  if (ctx->h_result) cudaFreeHost(ctx->h_result);
   delete ctx;
 }
 
@@ -185,30 +189,47 @@ int ecseg_segment_image(ecseg_ctx* ctx, const void* d_img, int h, int w, int ch,
   return ECSEG_OK;
 }
 
-int ecseg_segment_image_host(ecseg_ctx* ctx, const void* h_img, int h, int w, int ch, int bytes_per_sample,
-                             uint8_t* h_dapi, uint8_t* h_labels, int32_t* n_ec, int64_t* ec_px, int flags) {
+int ecseg_segment_image_host_async(ecseg_ctx* ctx, const void* h_img, int h, int w, int ch, int bytes_per_sample,
+                                   uint8_t* h_dapi, uint8_t* h_labels, int flags, void* stream) {
   API_GUARD(ctx);
   ECSEG_TRY(check_hw(ctx, h, w, "ecseg_segment_image_host"));
   if (!h_img || !h_labels || (ch != 1 && ch != 3 && ch != 4) || (bytes_per_sample != 1 && bytes_per_sample != 2)) {
     ctx->err = "ecseg_segment_image_host: bad arguments";
     return ECSEG_E_INVALID;
   }
-  cudaStream_t st = 0;
+  cudaStream_t st = (cudaStream_t)stream;
   const size_t n_px = (size_t)h * w;
   ECSEG_CUDA(cudaMemcpyAsync(ctx->img_in, h_img, n_px * ch * bytes_per_sample, cudaMemcpyHostToDevice, st));
   ECSEG_TRY(ecseg_segment_image(ctx, ctx->img_in, h, w, ch, bytes_per_sample, h_dapi ? ctx->dapi : nullptr, ctx->labels,
                                 ctx->d_n_ec, ctx->d_ec_px, flags, st));
   ECSEG_CUDA(cudaMemcpyAsync(h_labels, ctx->labels, n_px, cudaMemcpyDeviceToHost, st));
   if (h_dapi) ECSEG_CUDA(cudaMemcpyAsync(h_dapi, ctx->dapi, n_px, cudaMemcpyDeviceToHost, st));
-  int32_t n = 0; int64_t px = 0; int dev_err = 0;
-  ECSEG_CUDA(cudaMemcpyAsync(&n, ctx->d_n_ec, 4, cudaMemcpyDeviceToHost, st));
-  ECSEG_CUDA(cudaMemcpyAsync(&px, ctx->d_ec_px, 8, cudaMemcpyDeviceToHost, st));
-  ECSEG_CUDA(cudaMemcpyAsync(&dev_err, &ctx->counters->device_error, 4, cudaMemcpyDeviceToHost, st));
-  ECSEG_CUDA(cudaStreamSynchronize(st));
-  if (dev_err) { ctx->err = "tcgen05 pipeline watchdog fired (code " + std::to_string(dev_err) + ")"; return ECSEG_E_DEVICE; }
-  if (n_ec) *n_ec = n;
-  if (ec_px) *ec_px = px;
+  ECSEG_CUDA(cudaMemcpyAsync(&ctx->h_result->n_ec, ctx->d_n_ec, 4, cudaMemcpyDeviceToHost, st));
+  ECSEG_CUDA(cudaMemcpyAsync(&ctx->h_result->ec_px, ctx->d_ec_px, 8, cudaMemcpyDeviceToHost, st));
+  ECSEG_CUDA(cudaMemcpyAsync(&ctx->h_result->device_error, &ctx->counters->device_error, 4, cudaMemcpyDeviceToHost, st));
+  ECSEG_CUDA(cudaEventRecord(ctx->ev_done, st));
+  ctx->pending = true;
   return ECSEG_OK;
+}
+
+int ecseg_segment_image_host_wait(ecseg_ctx* ctx, int32_t* n_ec, int64_t* ec_px) {
+  API_GUARD(ctx);
+  if (!ctx->pending) { ctx->err = "ecseg_segment_image_host_wait: nothing in flight"; return ECSEG_E_STATE; }
+  ECSEG_CUDA(cudaEventSynchronize(ctx->ev_done));
+  ctx->pending = false;
+  if (ctx->h_result->device_error) {
+    ctx->err = "tcgen05 pipeline watchdog fired (code " + std::to_string(ctx->h_result->device_error) + ")";
+    return ECSEG_E_DEVICE;
+  }
+  if (n_ec) *n_ec = ctx->h_result->n_ec;
+  if (ec_px) *ec_px = ctx->h_result->ec_px;
+  return ECSEG_OK;
+}
+
+int ecseg_segment_image_host(ecseg_ctx* ctx, const void* h_img, int h, int w, int ch, int bytes_per_sample,
+                             uint8_t* h_dapi, uint8_t* h_labels, int32_t* n_ec, int64_t* ec_px, int flags) {
+  ECSEG_TRY(ecseg_segment_image_host_async(ctx, h_img, h, w, ch, bytes_per_sample, h_dapi, h_labels, flags, nullptr));
+  return ecseg_segment_image_host_wait(ctx, n_ec, ec_px);
 }
 
 int ecseg_debug_layer_output(ecseg_ctx* ctx, int layer, int n, float* d_out, void* stream) {

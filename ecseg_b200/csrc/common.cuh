@@ -86,6 +86,12 @@ struct ecseg_ctx {
   int32_t* d_n_ec = nullptr;
   int64_t* d_ec_px = nullptr;
 
+  // pinned result slot + completion event of the asynchronous host entry
+  struct HostResult { int32_t n_ec; int32_t device_error; int64_t ec_px; };
+  HostResult* h_result = nullptr;
+  cudaEvent_t ev_done = nullptr;
+  bool pending = false;
+
   ecseg::UNet* net = nullptr;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;

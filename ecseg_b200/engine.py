@@ -181,12 +181,16 @@ class Engine:
         return out
 
     # -- whole image ----------------------------------------------------------------------------
-    def segment_device(self, img: torch.Tensor, h: int, w: int, ch: int, bps: int, faithful_merge=False):
-        """Device-resident path: returns (labels, dapi, n_ec tensor, ec_px tensor) without syncing."""
-        labels = torch.empty((h, w), dtype=torch.uint8, device=self.device)
-        dapi = torch.empty_like(labels)
-        n = torch.zeros(1, dtype=torch.int32, device=self.device)
-        px = torch.zeros(1, dtype=torch.int64, device=self.device)
+    def segment_device(self, img: torch.Tensor, h: int, w: int, ch: int, bps: int, faithful_merge=False, out=None):
+        """Device-resident path: returns (labels, dapi, n_ec tensor, ec_px tensor) without syncing.
+        `out` = preallocated (labels, dapi, n, px) device tensors to write into."""
+        if out is not None:
+            labels, dapi, n, px = out
+        else:
+            labels = torch.empty((h, w), dtype=torch.uint8, device=self.device)
+            dapi = torch.empty_like(labels)
+            n = torch.zeros(1, dtype=torch.int32, device=self.device)
+            px = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._chk(self.lib.ecseg_segment_image(self.ctx, img.data_ptr(), h, w, ch, bps, dapi.data_ptr(),
                                                labels.data_ptr(), n.data_ptr(), px.data_ptr(),
                                                PP_FAITHFUL_MERGE if faithful_merge else 0, self._stream()))
@@ -207,6 +211,22 @@ class Engine:
             dapi_out.ctypes.data_as(c_void_p) if dapi_out is not None else None,
             labels_out.ctypes.data_as(c_void_p), byref(n), byref(px), PP_FAITHFUL_MERGE if faithful_merge else 0))
         return labels_out, n.value, px.value
+
+    def segment_host_async(self, img: np.ndarray, labels_out: np.ndarray, dapi_out: np.ndarray | None = None,
+                           faithful_merge=False):
+        """Enqueue one image (H2D, whole path, D2H) on the current stream; pair with segment_host_wait().
+        `img` / `labels_out` / `dapi_out` must stay alive (ideally pinned) until the wait returns."""
+        h, w = img.shape[:2]
+        ch = 1 if img.ndim == 2 else img.shape[2]
+        self._chk(self.lib.ecseg_segment_image_host_async(
+            self.ctx, img.ctypes.data_as(c_void_p), h, w, ch, img.dtype.itemsize,
+            dapi_out.ctypes.data_as(c_void_p) if dapi_out is not None else None,
+            labels_out.ctypes.data_as(c_void_p), PP_FAITHFUL_MERGE if faithful_merge else 0, self._stream()))
+
+    def segment_host_wait(self):
+        n, px = c_int32(), c_int64()
+        self._chk(self.lib.ecseg_segment_image_host_wait(self.ctx, byref(n), byref(px)))
+        return n.value, px.value
 
     def last_stage_ms(self):
         ms = (c_float * 4)()

@@ -124,6 +124,14 @@ int ecseg_segment_image(ecseg_ctx* ctx, const void* d_img, int h, int w, int ch,
 int ecseg_segment_image_host(ecseg_ctx* ctx, const void* h_img, int h, int w, int ch, int bytes_per_sample,
                              uint8_t* h_dapi, uint8_t* h_labels, int32_t* n_ec, int64_t* ec_px, int flags);
 
+/* Asynchronous pair of the call above for pipelining images over several contexts / streams (one
+ * image in flight per context): _async enqueues H2D copy, the whole path and the D2H copies on
+ * `stream` and returns; _wait blocks until that image is done and returns its count tuple.
+ * h_img / h_labels / h_dapi must stay valid (and should be pinned) until _wait returns. */
+int ecseg_segment_image_host_async(ecseg_ctx* ctx, const void* h_img, int h, int w, int ch, int bytes_per_sample,
+                                   uint8_t* h_dapi, uint8_t* h_labels, int flags, void* stream);
+int ecseg_segment_image_host_wait(ecseg_ctx* ctx, int32_t* n_ec, int64_t* ec_px);
+
 /* ---- introspection used by tests and bench.py ----------------------------------------------- */
 
 /* Copy the activation a U-Net layer produced in the last forward as float32 NHWC
