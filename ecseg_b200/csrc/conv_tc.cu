@@ -68,7 +68,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
   const uint32_t o_base = b_base + BS * kBBytes;                 // 2 output staging tiles
   const uint32_t q_base = o_base + 2 * kOutStage;                // 2 pooled staging tiles
   float* s_bias = reinterpret_cast<float*>(smem + AS * kAStride + BS * kBBytes + 2 * kOutStage + 2 * kPoolStage);
-  const uint32_t bar_base = q_base + 2 * kPoolStage + kMaxCout * 4;
+  const uint32_t s_bias_u32 = q_base + 2 * kPoolStage;
+  const uint32_t bar_base = s_bias_u32 + kMaxCout * 4;
   auto full_a = [&](int s) { return bar_base + 8u * s; };
   auto empty_a = [&](int s) { return bar_base + 8u * (AS + s); };
   auto full_b = [&](int s) { return bar_base + 8u * (2 * AS + s); };
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
             named_bar_sync(1, 128);
             const uint32_t so = o_base + buf * kOutStage + (uint32_t)m * 128u;
             const uint32_t sq = q_base + buf * kPoolStage + (uint32_t)pm * 128u;
-            const float* bs = s_bias + nch * N_TILE + sl * 64;
+            const uint32_t bs = s_bias_u32 + (uint32_t)(nch * N_TILE + sl * 64) * 4u;
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
               uint32_t v[32];
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
               float f[32];
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bs + cc * 32 + j);
+                const float4 b4 = ld_shared_f4(bs + (uint32_t)(cc * 32 + j) * 4u);
                 f[j] = __uint_as_float(v[j]) + b4.x;         f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
                 f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
               }

@@ -75,128 +75,210 @@ __device__ __forceinline__ void uf_union(int32_t* L, int a, int b) {
 static inline dim3 px_grid(int h, int w) { return dim3(cdiv(w, 32), cdiv(h, 8)); }
 static inline dim3 px_block() { return dim3(32, 8); }
 
-__global__ void k_pp_zero(Counters* c) {
-  if (threadIdx.x < 4) { c->ncomp[threadIdx.x] = 0; c->npix[threadIdx.x] = 0; }
-  if (threadIdx.x == 0) { c->n_chrom = 0; c->n_nuc = 0; c->last_root = -1; }
+// ------------------------------------------------------------------------------------------------
+// Connected-component labelling in three passes:
+//   k_ccl_tile    one block per 32x32 tile: horizontal runs by warp ballot, vertical / diagonal unions
+//                 with atomicMin on SHARED-memory labels, then every pixel is written once to global
+//                 memory pointing at its tile-local root (global linear index).  Tile roots reset their
+//                 statistics slots.  Global memory sees 1 B read + 4 B written per pixel and no atomics.
+//   k_ccl_border  only the pixels on tile borders (1/16 of the image) union across tiles with global
+//                 atomicMin.
+//   k_ccl_finish  every pixel resolves its final root (tile root -> short chain), optional per-component
+//                 area / coordinate sums (warp-aggregated), root and pixel counts.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCclTile = 32;
+
+__device__ __forceinline__ int ufs_find(const int* sl, int a) {
+  int p = sl[a];
+  while (p != a) { a = p; p = sl[a]; }
+  return a;
+}
+__device__ __forceinline__ void ufs_union(int* sl, int a, int b) {
+  bool done = false;
+  while (!done) {
+    a = ufs_find(sl, a);
+    b = ufs_find(sl, b);
+    if (a < b) { int old = atomicMin(sl + b, a); done = (old == b); b = old; }
+    else if (b < a) { int old = atomicMin(sl + a, b); done = (old == a); a = old; }
+    else done = true;
+  }
 }
 
-// Pass 1: L[i] = index of the head of pixel i's horizontal run inside its 32-pixel segment.
-__global__ void k_ccl_init(const uint8_t* __restrict__ cls, int h, int w, int mode, int c, int32_t* __restrict__ L) {
-  PIXEL_XY();
-  const bool in = x < w;
-  const int k = in ? key_of(cls[(size_t)y * w + x], mode, c) : 0;
-  const int kl = __shfl_up_sync(0xffffffffu, k, 1);
-  const bool same = threadIdx.x > 0 && kl == k;
-  const unsigned heads = ~__ballot_sync(0xffffffffu, same);
-  if (!in) return;
-  const unsigned m = heads & (0xffffffffu >> (31 - threadIdx.x));
-  const int head = 31 - __clz(m);
-  L[(size_t)y * w + x] = k ? (y * w + blockIdx.x * 32 + head) : -1;
-}
-
-// Pass 2: union across segment boundaries and with the row above; only run heads (and pixels
-// whose upper-left neighbour differs) issue a union, everything else is implied by the run links.
-__global__ void k_ccl_merge(const uint8_t* __restrict__ cls, int h, int w, int mode, int c, int conn8,
-                            int32_t* __restrict__ L) {
-  PIXEL_XY();
-  if (x >= w) return;
-  const int i = y * w + x;
-  const int k = key_of(cls[i], mode, c);
-  if (!k) return;
-  const bool left_same = x > 0 && key_of(cls[i - 1], mode, c) == k;
-  if (threadIdx.x == 0 && left_same) uf_union(L, i, i - 1);
-  if (y == 0) return;
-  const bool run_head = threadIdx.x == 0 || !left_same;
-  const bool up_same = key_of(cls[i - w], mode, c) == k;
-  const bool nw_same = x > 0 && key_of(cls[i - w - 1], mode, c) == k;
-  if (up_same) {
-    if (run_head || !nw_same) uf_union(L, i, i - w);
-  } else if (conn8) {
-    if (run_head && nw_same) uf_union(L, i, i - w - 1);
-    if (x < w - 1) {
-      const bool right_same = key_of(cls[i + 1], mode, c) == k;
-      if (!right_same && key_of(cls[i - w + 1], mode, c) == k) uf_union(L, i, i - w + 1);
+__global__ void __launch_bounds__(256) k_ccl_tile(const uint8_t* __restrict__ cls, int h, int w, int mode, int c, int conn8,
+                                                  int32_t* __restrict__ L, int32_t* __restrict__ area,
+                                                  unsigned long long* __restrict__ sy, unsigned long long* __restrict__ sx,
+                                                  int32_t* __restrict__ flag, Counters* __restrict__ cnt) {
+  __shared__ uint8_t sk[kCclTile][kCclTile + 4];
+  __shared__ int sl[kCclTile * kCclTile];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * kCclTile, y0 = blockIdx.y * kCclTile;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4) {     // per-run counters (k_ccl_finish runs later)
+    cnt->ncomp[threadIdx.x] = 0; cnt->npix[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { cnt->n_chrom = 0; cnt->n_nuc = 0; cnt->last_root = -1; }
+  }
+  const int x = x0 + lane;
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    const int row = wp + 8 * ps, y = y0 + row;
+    const int k = (y < h && x < w) ? key_of(cls[(size_t)y * w + x], mode, c) : 0;
+    sk[row][lane] = (uint8_t)k;
+    const int kl = __shfl_up_sync(0xffffffffu, k, 1);
+    const bool same = lane > 0 && kl == k;
+    const unsigned heads = ~__ballot_sync(0xffffffffu, same);
+    const int head = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+    sl[row * 32 + lane] = row * 32 + head;      // background pixels form runs too; they are never unioned vertically
+  }
+  __syncthreads();
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    const int row = wp + 8 * ps;
+    const int k = sk[row][lane];
+    if (k && row > 0) {
+      const int i = row * 32 + lane;
+      const bool left_same = lane > 0 && sk[row][lane - 1] == k;
+      const bool up_same = sk[row - 1][lane] == k;
+      const bool nw_same = lane > 0 && sk[row - 1][lane - 1] == k;
+      if (up_same) {
+        if (!left_same || !nw_same) ufs_union(sl, i, i - 32);
+      } else if (conn8) {
+        if (!left_same && nw_same) ufs_union(sl, i, i - 33);
+        if (lane < 31 && sk[row][lane + 1] != k && sk[row - 1][lane + 1] == k) ufs_union(sl, i, i - 31);
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    const int row = wp + 8 * ps, y = y0 + row;
+    if (y < h && x < w) {
+      const int i = row * 32 + lane;
+      const size_t gi = (size_t)y * w + x;
+      if (sk[row][lane]) {
+        const int r = ufs_find(sl, i);
+        L[gi] = (y0 + (r >> 5)) * w + x0 + (r & 31);
+        if (r == i) { area[gi] = 0; sy[gi] = 0ull; sx[gi] = 0ull; flag[gi] = 0; }
+      } else {
+        L[gi] = -1;
+      }
     }
   }
 }
 
-// Pass 3: point every pixel at its root; roots reset their statistics slot and are counted.
-__global__ void k_ccl_flatten(const uint8_t* __restrict__ cls, int h, int w, int mode, int c, int32_t* __restrict__ L,
-                              int32_t* __restrict__ area, unsigned long long* __restrict__ sy,
-                              unsigned long long* __restrict__ sx, int32_t* __restrict__ flag,
-                              Counters* __restrict__ cnt) {
-  __shared__ unsigned int s_fg;
-  if (threadIdx.x == 0 && threadIdx.y == 0) s_fg = 0;
+// Unions across tile borders.  Thread t < n_hb*w handles a pixel of a tile's top row (neighbours in the row
+// above), the rest a pixel of a tile's left column (neighbours in the column to the left).
+__global__ void k_ccl_border(const uint8_t* __restrict__ cls, int h, int w, int mode, int c, int conn8,
+                             int32_t* __restrict__ L) {
+  const int n_hb = (h - 1) / kCclTile, n_vb = (w - 1) / kCclTile;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n_h = (long long)n_hb * w;
+  if (t < n_h) {
+    const int y = kCclTile * (1 + (int)(t / w)), x = (int)(t % w);
+    const int i = y * w + x;
+    const int k = key_of(cls[i], mode, c);
+    if (!k) return;
+    if (key_of(cls[i - w], mode, c) == k) { uf_union(L, i, i - w); return; }
+    if (!conn8) return;
+    if (x > 0 && key_of(cls[i - w - 1], mode, c) == k) uf_union(L, i, i - w - 1);
+    if (x < w - 1 && key_of(cls[i - w + 1], mode, c) == k) uf_union(L, i, i - w + 1);
+  } else {
+    const long long u = t - n_h;
+    if (u >= (long long)n_vb * h) return;
+    const int x = kCclTile * (1 + (int)(u / h)), y = (int)(u % h);
+    const int i = y * w + x;
+    const int k = key_of(cls[i], mode, c);
+    if (!k) return;
+    if (key_of(cls[i - 1], mode, c) == k) { uf_union(L, i, i - 1); return; }
+    if (!conn8) return;
+    if (y > 0 && key_of(cls[i - w - 1], mode, c) == k) uf_union(L, i, i - w - 1);
+    if (y < h - 1 && key_of(cls[i + w - 1], mode, c) == k) uf_union(L, i, i + w - 1);
+  }
+}
+
+enum { FIN_AREA = 1, FIN_CENTROID = 2, FIN_CLASS_PIX = 4, FIN_LAST_ROOT = 8 };
+
+// Final roots + reductions.  Roots are pixels with L[i] == i (root entries are stable once the unions are done).
+__global__ void __launch_bounds__(256) k_ccl_finish(const uint8_t* __restrict__ cls, int h, int w, int mode, int c, int what,
+                                                    int32_t* __restrict__ L, int32_t* __restrict__ area,
+                                                    unsigned long long* __restrict__ sy, unsigned long long* __restrict__ sx,
+                                                    Counters* __restrict__ cnt) {
+  __shared__ unsigned int s_fg, s_cls[4], s_roots[4];
+  __shared__ int s_last;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (tid < 4) { s_cls[tid] = 0; s_roots[tid] = 0; }
+  if (tid == 0) { s_fg = 0; s_last = -1; }
   __syncthreads();
   const int x = blockIdx.x * 32 + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  bool fg = false;
+  int r = -1, v = 0, kroot = -1;
   if (y < h && x < w) {
     const int i = y * w + x;
-    if (L[i] >= 0) {
-      fg = true;
-      const int r = uf_find(L, i);
-      L[i] = r;
-      if (r == i) {
-        area[i] = 0; sy[i] = 0ull; sx[i] = 0ull; flag[i] = 0;
-        atomicAdd(&cnt->ncomp[key_of(cls[i], mode, c) & 3], 1);
-        atomicMax(&cnt->last_root, i);
-      }
+    const int l0 = L[i];
+    if (l0 >= 0) {
+      r = uf_find(L, l0);
+      if (r != l0) L[i] = r;
+      v = cls[i];
+      if (r == i) kroot = key_of((uint8_t)v, mode, c) & 3;
     }
   }
-  const unsigned b = __ballot_sync(0xffffffffu, fg);
-  if (threadIdx.x == 0 && b) atomicAdd(&s_fg, (unsigned)__popc(b));
-  __syncthreads();
-  if (threadIdx.x == 0 && threadIdx.y == 0 && s_fg) atomicAdd(&cnt->npix[0], (unsigned long long)s_fg);
-}
-
-// Per-component area (and optionally coordinate sums), warp-aggregated by root before the atomics;
-// per-class pixel totals are block-reduced.
-__global__ void k_ccl_accumulate(const uint8_t* __restrict__ cls, int h, int w, const int32_t* __restrict__ L,
-                                 int32_t* __restrict__ area, unsigned long long* __restrict__ sy,
-                                 unsigned long long* __restrict__ sx, int want_centroid, Counters* __restrict__ cnt) {
-  __shared__ unsigned int s_cls[4];
-  if (threadIdx.y == 0 && threadIdx.x < 4) s_cls[threadIdx.x] = 0;
-  __syncthreads();
-  const int x = blockIdx.x * 32 + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  int r = -1, v = 0;
-  if (y < h && x < w) { r = L[y * w + x]; v = cls[y * w + x]; }
   const bool valid = r >= 0;
   const unsigned act = __ballot_sync(0xffffffffu, valid);
-  if (valid) {
-    const unsigned peers = __match_any_sync(act, r);
-    if ((int)threadIdx.x == __ffs(peers) - 1) {
-      const int n = __popc(peers);
-      atomicAdd(area + r, n);
-      if (want_centroid) {
-        unsigned m = peers;
-        unsigned long long sxs = 0;
-        while (m) { sxs += (unsigned)(__ffs(m) - 1); m &= m - 1; }
-        atomicAdd(sy + r, (unsigned long long)n * (unsigned)y);
-        atomicAdd(sx + r, sxs + (unsigned long long)n * (unsigned)(blockIdx.x * 32));
+  if (threadIdx.x == 0 && act) atomicAdd(&s_fg, (unsigned)__popc(act));
+  if (what & (FIN_AREA | FIN_CENTROID)) {
+    if (valid) {
+      const unsigned peers = __match_any_sync(act, r);
+      if ((int)threadIdx.x == __ffs(peers) - 1) {
+        const int n = __popc(peers);
+        atomicAdd(area + r, n);
+        if (what & FIN_CENTROID) {
+          unsigned m = peers;
+          unsigned long long sxs = 0;
+          while (m) { sxs += (unsigned)(__ffs(m) - 1); m &= m - 1; }
+          atomicAdd(sy + r, (unsigned long long)n * (unsigned)y);
+          atomicAdd(sx + r, sxs + (unsigned long long)n * (unsigned)(blockIdx.x * 32));
+        }
       }
     }
   }
+  // roots per key class (warp-aggregated), raster-last root
 #pragma unroll
-  for (int k = 1; k < 4; ++k) {
-    const unsigned b = __ballot_sync(0xffffffffu, v == k);
-    if (threadIdx.x == 0 && b) atomicAdd(&s_cls[k], (unsigned)__popc(b));
+  for (int k = 0; k < 4; ++k) {
+    const unsigned b = __ballot_sync(0xffffffffu, kroot == k);
+    if (threadIdx.x == 0 && b) atomicAdd(&s_roots[k], (unsigned)__popc(b));
+  }
+  if (what & FIN_LAST_ROOT) {
+    int lr = kroot >= 0 ? y * w + x : -1;
+    for (int o = 16; o > 0; o >>= 1) lr = max(lr, __shfl_xor_sync(0xffffffffu, lr, o));
+    if (threadIdx.x == 0 && lr >= 0) atomicMax(&s_last, lr);
+  }
+  if (what & FIN_CLASS_PIX) {
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const unsigned b = __ballot_sync(0xffffffffu, v == k);
+      if (threadIdx.x == 0 && b) atomicAdd(&s_cls[k], (unsigned)__popc(b));
+    }
   }
   __syncthreads();
-  if (threadIdx.y == 0 && threadIdx.x > 0 && threadIdx.x < 4 && s_cls[threadIdx.x])
-    atomicAdd(&cnt->npix[threadIdx.x], (unsigned long long)s_cls[threadIdx.x]);
+  if (tid < 4) {
+    if (s_roots[tid]) atomicAdd(&cnt->ncomp[tid], (int)s_roots[tid]);
+    if (tid > 0 && s_cls[tid]) atomicAdd(&cnt->npix[tid], (unsigned long long)s_cls[tid]);
+  }
+  if (tid == 0) {
+    if (s_fg) atomicAdd(&cnt->npix[0], (unsigned long long)s_fg);
+    if (s_last >= 0) atomicMax(&cnt->last_root, s_last);
+  }
 }
 
-static int ccl_run(ecseg_ctx* ctx, const uint8_t* cls, int h, int w, int mode, int c, int conn8, cudaStream_t st) {
-  k_pp_zero<<<1, 32, 0, st>>>(ctx->counters);
+static int ccl_run(ecseg_ctx* ctx, const uint8_t* cls, int h, int w, int mode, int c, int conn8, int what, cudaStream_t st) {
+  k_ccl_tile<<<dim3(cdiv(w, kCclTile), cdiv(h, kCclTile)), 256, 0, st>>>(cls, h, w, mode, c, conn8, ctx->L, ctx->area,
+                                                                          ctx->sum_y, ctx->sum_x, ctx->flag, ctx->counters);
   ECSEG_CHECK_LAUNCH();
-  k_ccl_init<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, mode, c, ctx->L);
-  ECSEG_CHECK_LAUNCH();
-  k_ccl_merge<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, mode, c, conn8, ctx->L);
-  ECSEG_CHECK_LAUNCH();
-  k_ccl_flatten<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, mode, c, ctx->L, ctx->area, ctx->sum_y,
-                                                      ctx->sum_x, ctx->flag, ctx->counters);
+  const long long nb = (long long)((h - 1) / kCclTile) * w + (long long)((w - 1) / kCclTile) * h;
+  if (nb > 0) {
+    k_ccl_border<<<cdiv(nb, 256), 256, 0, st>>>(cls, h, w, mode, c, conn8, ctx->L);
+    ECSEG_CHECK_LAUNCH();
+  }
+  k_ccl_finish<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, mode, c, what, ctx->L, ctx->area, ctx->sum_y, ctx->sum_x,
+                                                     ctx->counters);
   ECSEG_CHECK_LAUNCH();
   return ECSEG_OK;
 }
@@ -227,7 +309,7 @@ __global__ void k_fill_apply(uint8_t* __restrict__ cls, int h, int w, const int3
 }
 
 int pp_fill_holes(ecseg_ctx* ctx, uint8_t* cls, int h, int w, int c, cudaStream_t st) {
-  ECSEG_TRY(ccl_run(ctx, cls, h, w, KEY_NE, c, /*conn8=*/0, st));
+  ECSEG_TRY(ccl_run(ctx, cls, h, w, KEY_NE, c, /*conn8=*/0, 0, st));
   k_mark_border<<<cdiv(2 * (h + w), 256), 256, 0, st>>>(ctx->L, h, w, ctx->flag);
   ECSEG_CHECK_LAUNCH();
   k_fill_apply<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, ctx->L, ctx->flag, c);
@@ -260,10 +342,7 @@ __global__ void k_size_apply(uint8_t* __restrict__ cls, int h, int w, const int3
 }
 
 int pp_size_thresh(ecseg_ctx* ctx, uint8_t* cls, int h, int w, cudaStream_t st) {
-  ECSEG_TRY(ccl_run(ctx, cls, h, w, KEY_CLASS, 0, /*conn8=*/1, st));
-  k_ccl_accumulate<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, ctx->L, ctx->area, ctx->sum_y, ctx->sum_x, 0,
-                                                         ctx->counters);
-  ECSEG_CHECK_LAUNCH();
+  ECSEG_TRY(ccl_run(ctx, cls, h, w, KEY_CLASS, 0, /*conn8=*/1, FIN_AREA | FIN_CLASS_PIX, st));
   k_size_apply<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, ctx->L, ctx->area, ctx->counters);
   ECSEG_CHECK_LAUNCH();
   return ECSEG_OK;
@@ -363,10 +442,7 @@ __global__ void k_nucleus_apply(uint8_t* __restrict__ cls, int h, int w, const i
 }
 
 static int pp_nucleus_in_metaphase(ecseg_ctx* ctx, uint8_t* cls, int h, int w, cudaStream_t st) {
-  ECSEG_TRY(ccl_run(ctx, cls, h, w, KEY_CLASS, 0, /*conn8=*/1, st));
-  k_ccl_accumulate<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, ctx->L, ctx->area, ctx->sum_y, ctx->sum_x, 1,
-                                                         ctx->counters);
-  ECSEG_CHECK_LAUNCH();
+  ECSEG_TRY(ccl_run(ctx, cls, h, w, KEY_CLASS, 0, /*conn8=*/1, FIN_AREA | FIN_CENTROID, st));
   k_compact_centroids<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, ctx->L, ctx->area, ctx->sum_y, ctx->sum_x,
                                                             ctx->chrom_cy, ctx->chrom_cx, ctx->nuc_roots, ctx->counters);
   ECSEG_CHECK_LAUNCH();
@@ -432,7 +508,7 @@ __global__ void k_open_apply(uint8_t* __restrict__ cls, const uint8_t* __restric
 int pp_merge_comp(ecseg_ctx* ctx, uint8_t* cls, int h, int w, int c, cudaStream_t st) {
   if (c != 1 && c != 2) { ctx->err = "merge_comp: class_id must be 1 or 2"; return ECSEG_E_INVALID; }
   const int mask_id = (c == 1) ? 2 : 1;
-  ECSEG_TRY(ccl_run(ctx, cls, h, w, KEY_NZ_EXCEPT, mask_id, /*conn8=*/1, st));
+  ECSEG_TRY(ccl_run(ctx, cls, h, w, KEY_NZ_EXCEPT, mask_id, /*conn8=*/1, FIN_LAST_ROOT, st));
   k_mark_has_class<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, ctx->L, ctx->flag, c);
   ECSEG_CHECK_LAUNCH();
   k_merge_convert<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, ctx->L, ctx->flag, c, ctx->counters);
@@ -460,7 +536,7 @@ __global__ void k_count_finish(const Counters* __restrict__ cnt, long long n_px,
 
 static int count_mode(ecseg_ctx* ctx, const uint8_t* cls, int h, int w, int mode, int c, int32_t* d_n, int64_t* d_px,
                       cudaStream_t st) {
-  ECSEG_TRY(ccl_run(ctx, cls, h, w, mode, c, /*conn8=*/1, st));
+  ECSEG_TRY(ccl_run(ctx, cls, h, w, mode, c, /*conn8=*/1, 0, st));
   k_count_finish<<<1, 32, 0, st>>>(ctx->counters, (long long)h * w, d_n, d_px);
   ECSEG_CHECK_LAUNCH();
   return ECSEG_OK;
@@ -480,7 +556,7 @@ __global__ void k_label_export(const int32_t* __restrict__ L, int n, int32_t* __
 
 int pp_label(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w, int conn, int32_t* d_out, cudaStream_t st) {
   if (conn != 4 && conn != 8) { ctx->err = "label: connectivity must be 4 or 8"; return ECSEG_E_INVALID; }
-  ECSEG_TRY(ccl_run(ctx, d_mask, h, w, KEY_CLASS, 0, conn == 8, st));
+  ECSEG_TRY(ccl_run(ctx, d_mask, h, w, KEY_CLASS, 0, conn == 8, 0, st));
   k_label_export<<<cdiv((long long)h * w, 256), 256, 0, st>>>(ctx->L, h * w, d_out);
   ECSEG_CHECK_LAUNCH();
   return ECSEG_OK;

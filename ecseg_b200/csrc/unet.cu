@@ -531,8 +531,12 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   const int out_hw = kTile >> l.level;
   const int in_hw = l.convT ? out_hw / 2 : out_hw;
   const int rows = net->cout_rows[li];
-  int n_tile = l.convT ? 64 : (rows < net->tc_ntile_max ? rows : net->tc_ntile_max);
-  if (n_tile > 256) n_tile = 256;
+  // N tile: 256 halves the weight re-fetch per MMA but uses all of TMEM (epilogue not overlapped) and gives
+  // coarser work items; 128 double-buffers the accumulators.  Measured per layer (profiles/r01_launches_v4*.txt):
+  // 128 wins for the short-K / many-block layers of levels 2-3, 256 for level 4 and the 512-channel concat conv.
+  int n_tile = l.convT ? 64 : (rows < 256 ? rows : 256);
+  if (!l.convT && rows >= 256 && (li == 4 || li == 5 || li == 6 || li == 7 || li == 15)) n_tile = 128;
+  if (n_tile > net->tc_ntile_max) n_tile = net->tc_ntile_max;
   const int cs = net->tc_cluster;
   const size_t pin = kBufs[wr.in].ch, pout = kBufs[wr.out].ch;
   ECSEG_TRY(make_tm_nhwc(ctx, &p.tm_a, net->buf[wr.in], l.cin, in_hw, in_hw, NT, pin, pin * in_hw, pin * in_hw * in_hw, 18, 18, bf16));
