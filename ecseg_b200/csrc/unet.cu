@@ -136,21 +136,29 @@ __global__ void __launch_bounds__(256) k_conv_first(const uint8_t* __restrict__ 
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) b[j] = __ldg(bias + cg + j);
+  // input patch of the block (kFirstRows+2 rows x 34 columns) converted to float once, in shared memory;
   // 'same' padding at the TILE border (tile-wise semantics): out-of-tile taps read as 0
-  auto row = [&](int yy, float v[3]) {
-    const bool in = yy >= 0 && yy < kTile;
-    const uint8_t* r = src + (size_t)(in ? yy : 0) * pitch + x;
-    v[0] = (in && x > 0) ? (float)r[-1] : 0.f;
-    v[1] = in ? (float)r[0] : 0.f;
-    v[2] = (in && x < kTile - 1) ? (float)r[1] : 0.f;
-  };
+  __shared__ float s_in[kFirstRows + 2][36];
+  {
+    const int xb = blockIdx.x * 32 - 1;
+    for (int e = threadIdx.x; e < (kFirstRows + 2) * 34; e += 256) {
+      const int r = e / 34, cidx = e % 34;
+      const int yy = y0 - 1 + r, xx = xb + cidx;
+      float v = 0.f;
+      if (yy >= 0 && yy < kTile && xx >= 0 && xx < kTile) v = (float)src[(size_t)yy * pitch + xx];
+      s_in[r][cidx] = v;
+    }
+  }
+  __syncthreads();
+  const int xl = threadIdx.x >> 3;
+  auto row = [&](int r, float v[3]) { v[0] = s_in[r][xl]; v[1] = s_in[r][xl + 1]; v[2] = s_in[r][xl + 2]; };
   float win[3][3];
-  row(y0 - 1, win[0]);
-  row(y0, win[1]);
+  row(0, win[0]);
+  row(1, win[1]);
   T* dst = out + (((size_t)img * kTile + y0) * kTile + x) * 64 + cg;
 #pragma unroll 4
   for (int dy = 0; dy < kFirstRows; ++dy) {
-    row(y0 + dy + 1, win[2]);
+    row(dy + 2, win[2]);
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = b[j];
