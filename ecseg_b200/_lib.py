@@ -31,6 +31,10 @@ SIGNATURES = {
     "ecseg_size_thresh": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "ecseg_merge_comp": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ecseg_label": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ecseg_overlay_counts": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                     c_void_p, c_void_p]),
+    "ecseg_count_colocalization": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "ecseg_remove_small_objects": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ecseg_segment_image": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_int, c_void_p]),
     "ecseg_segment_image_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

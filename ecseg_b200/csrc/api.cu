@@ -167,6 +167,30 @@ int ecseg_label(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w, int connect
   return pp_label(ctx, d_mask, h, w, connectivity, d_out, (cudaStream_t)stream);
 }
 
+int ecseg_overlay_counts(ecseg_ctx* ctx, const void* d_img, int h, int w, int ch, int bytes_per_sample,
+                         const uint8_t* d_labels, int sensitivity, uint8_t* d_red_inv, uint8_t* d_green_inv, int64_t* d_out12,
+                         void* stream) {
+  API_GUARD(ctx);
+  ECSEG_TRY(check_hw(ctx, h, w, "ecseg_overlay_counts"));
+  return pp_overlay_counts(ctx, d_img, h, w, ch, bytes_per_sample, d_labels, sensitivity, d_red_inv, d_green_inv, d_out12,
+                           (cudaStream_t)stream);
+}
+
+int ecseg_count_colocalization(ecseg_ctx* ctx, const uint8_t* d_ob1, const uint8_t* d_ob2, int h, int w, int64_t* d_n,
+                               void* stream) {
+  API_GUARD(ctx);
+  ECSEG_TRY(check_hw(ctx, h, w, "ecseg_count_colocalization"));
+  if (!d_ob1 || !d_ob2 || !d_n) { ctx->err = "ecseg_count_colocalization: null pointer"; return ECSEG_E_INVALID; }
+  return pp_count_colocalization(ctx, d_ob1, d_ob2, h, w, d_n, (cudaStream_t)stream);
+}
+
+int ecseg_remove_small_objects(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w, int min_size, uint8_t* d_out, void* stream) {
+  API_GUARD(ctx);
+  ECSEG_TRY(check_hw(ctx, h, w, "ecseg_remove_small_objects"));
+  if (!d_mask || !d_out) { ctx->err = "ecseg_remove_small_objects: null pointer"; return ECSEG_E_INVALID; }
+  return pp_remove_small_objects(ctx, d_mask, h, w, min_size, d_out, (cudaStream_t)stream);
+}
+
 int ecseg_segment_image(ecseg_ctx* ctx, const void* d_img, int h, int w, int ch, int bytes_per_sample, uint8_t* d_dapi,
                         uint8_t* d_labels, int32_t* d_n_ec, int64_t* d_ec_px, int flags, void* stream) {
   API_GUARD(ctx);

@@ -18,6 +18,7 @@ constexpr int kClasses = 4;     // NUM_CLASSES              (src/image_tools.py:
 constexpr int kEcSizeThreshold = 15;  // EC_SIZE_THRESHOLD  (src/image_tools.py:13)
 constexpr int kMinChromCount = 5;     // src/image_tools.py:72
 constexpr double kChromWindow = 70.0; // src/image_tools.py:72
+constexpr int kHsrSizeThreshold = 20; // HSR_SIZE_THRESHOLD  (src/meta_overlay.py:12)
 
 // Small device-resident scalar block, zeroed per stage by k_zero_counters.
 struct Counters {
@@ -32,7 +33,7 @@ struct Counters {
   int last_root;                   // merge_comp: highest component root (raster-last component)
   int range_error;                 // img_as_ubyte range violation seen
   int device_error;                // tcgen05 pipeline watchdog
-  int pad;
+  int ov_hits[4];                  // meta_overlay: components flagged per colocalisation test
 };
 
 struct TileGrid {
@@ -141,6 +142,12 @@ int pp_fill_holes(ecseg_ctx* ctx, uint8_t* d_labels, int h, int w, int class_id,
 int pp_size_thresh(ecseg_ctx* ctx, uint8_t* d_labels, int h, int w, cudaStream_t st);
 int pp_merge_comp(ecseg_ctx* ctx, uint8_t* d_labels, int h, int w, int class_id, cudaStream_t st);
 int pp_label(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w, int conn, int32_t* d_out, cudaStream_t st);
+int pp_overlay_counts(ecseg_ctx* ctx, const void* d_img, int h, int w, int ch, int bps, const uint8_t* d_labels, int sens,
+                      uint8_t* d_red_inv, uint8_t* d_green_inv, int64_t* d_out, cudaStream_t st);
+int pp_count_colocalization(ecseg_ctx* ctx, const uint8_t* d_ob1, const uint8_t* d_ob2, int h, int w, int64_t* d_out,
+                            cudaStream_t st);
+int pp_remove_small_objects(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w, int min_size, uint8_t* d_out,
+                            cudaStream_t st);
 
 int unet_create(ecseg_ctx* ctx);
 void unet_destroy(ecseg_ctx* ctx);

@@ -26,7 +26,8 @@ enum KeyMode {
   KEY_EQ = 1,         // key = (v == c)
   KEY_NE = 2,         // key = (v != c)
   KEY_NZ_EXCEPT = 3,  // key = (v != 0 && v != c)
-  KEY_NONZERO = 4     // key = (v != 0)
+  KEY_NONZERO = 4,    // key = (v != 0)
+  KEY_BITS = 5        // v is a bit field: key = all bits of (c & 0xff) set and no bit of (c >> 8) set
 };
 
 __device__ __forceinline__ int key_of(uint8_t v, int mode, int c) {
@@ -35,6 +36,7 @@ __device__ __forceinline__ int key_of(uint8_t v, int mode, int c) {
     case KEY_EQ: return v == c;
     case KEY_NE: return v != c;
     case KEY_NZ_EXCEPT: return v != 0 && v != c;
+    case KEY_BITS: return (v & (c & 0xff)) == (c & 0xff) && (v & (c >> 8)) == 0;
     default: return v != 0;
   }
 }
@@ -115,6 +117,7 @@ __global__ void __launch_bounds__(256) k_ccl_tile(const uint8_t* __restrict__ cl
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4) {     // per-run counters (k_ccl_finish runs later)
     cnt->ncomp[threadIdx.x] = 0; cnt->npix[threadIdx.x] = 0;
     if (threadIdx.x == 0) { cnt->n_chrom = 0; cnt->n_nuc = 0; cnt->last_root = -1; }
+    cnt->ov_hits[threadIdx.x] = 0;
   }
   const int x = x0 + lane;
 #pragma unroll
@@ -544,6 +547,163 @@ static int count_mode(ecseg_ctx* ctx, const uint8_t* cls, int h, int w, int mode
 
 int pp_count_cc(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w, int32_t* d_n, int64_t* d_px, cudaStream_t st) {
   return count_mode(ctx, d_mask, h, w, KEY_NONZERO, 0, d_n, d_px, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// meta_overlay  (src/meta_overlay.py:59-83; helpers src/image_tools.py:103-146)
+// ------------------------------------------------------------------------------------------------
+enum { OV_EC = 1, OV_CHROM = 2, OV_NUC = 4, OV_FISH = 8, OV_FISH2 = 16, OV_FISH_L = 32, OV_FISH2_L = 64 };
+#define OV_SEL(must, mustnot) ((must) | ((mustnot) << 8))
+
+__device__ __forceinline__ uint8_t ov_scale_u16(unsigned int v) {   // cv2.convertScaleAbs(alpha=255/65535)
+  const int q = __double2int_rn(__dmul_rn((double)v, 255.0 / 65535.0));
+  return (uint8_t)min(max(q, 0), 255);
+}
+
+// split_FISH_channels (image_tools.py:136-146) + read_seg masks (utils.py:125-132) + the nucleus mask-out
+// of meta_overlay.py:68,78 as one bit field per pixel; optionally the inverted red / green planes.
+template <typename T>
+__global__ void k_ov_bits(const T* __restrict__ img, int n_px, int ch, const uint8_t* __restrict__ labels, int sens,
+                          uint8_t* __restrict__ bits, uint8_t* __restrict__ red_inv, uint8_t* __restrict__ green_inv) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += gridDim.x * blockDim.x) {
+    const unsigned int rv = img[(size_t)i * ch], gv = img[(size_t)i * ch + 1];
+    const uint8_t r = sizeof(T) == 2 ? ov_scale_u16(rv) : (uint8_t)rv;
+    const uint8_t g = sizeof(T) == 2 ? ov_scale_u16(gv) : (uint8_t)gv;
+    const int lab = labels[i];
+    int b = lab == 3 ? OV_EC : lab == 2 ? OV_CHROM : lab == 1 ? OV_NUC : 0;
+    if (lab != 1) {
+      if (g > sens) b |= OV_FISH;      // first_fish = green  (meta_overlay.py:52,61)
+      if (r > sens) b |= OV_FISH2;     // second_fish = red
+    }
+    bits[i] = (uint8_t)b;
+    if (red_inv) red_inv[i] = 255 - r;
+    if (green_inv) green_inv[i] = 255 - g;
+  }
+}
+
+__global__ void k_ov_nonzero(const uint8_t* __restrict__ in, int n_px, uint8_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_px) out[i] = in[i] != 0;
+}
+
+// remove_small_objects(fish, min_size) on the labelled 4-connected components: survivors get `dst_bit`.
+__global__ void k_ov_keep_large(uint8_t* __restrict__ bits, int n_px, const int32_t* __restrict__ L,
+                                const int32_t* __restrict__ area, int min_size, int dst_bit) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_px) return;
+  const int r = L[i];
+  if (r >= 0 && area[r] >= min_size) bits[i] |= (uint8_t)dst_bit;
+}
+
+// flag[root] |= (1 << k) when a pixel of the component satisfies selector k of `other`
+__global__ void k_ov_flag(const uint8_t* __restrict__ other, int n_px, const int32_t* __restrict__ L,
+                          int32_t* __restrict__ flag, int sel0, int sel1, int sel2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_px) return;
+  const int r = L[i];
+  if (r < 0) return;
+  const uint8_t v = other[i];
+  int f = 0;
+  if (sel0 >= 0 && key_of(v, KEY_BITS, sel0)) f |= 1;
+  if (sel1 >= 0 && key_of(v, KEY_BITS, sel1)) f |= 2;
+  if (sel2 >= 0 && key_of(v, KEY_BITS, sel2)) f |= 4;
+  if (f && (flag[r] & f) != f) atomicOr(flag + r, f);
+}
+
+__global__ void k_ov_count_hits(int n_px, const int32_t* __restrict__ L, const int32_t* __restrict__ flag,
+                                Counters* __restrict__ cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = (i < n_px && L[i] == i) ? flag[i] : 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const unsigned b = __ballot_sync(0xffffffffu, (f >> k) & 1);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&cnt->ov_hits[k], __popc(b));
+  }
+}
+
+// count_cc tuple and colocalisation counts of the last labelling, with the np.unique(...)[1:] quirk:
+// a mask without any background pixel loses its (single) component.
+__global__ void k_ov_finish(const Counters* __restrict__ cnt, long long n_px, int64_t* __restrict__ out, int i_n, int i_px,
+                            int i_h0, int i_h1, int i_h2) {
+  if (threadIdx.x || blockIdx.x) return;
+  const int n = cnt->ncomp[1];
+  const long long px = (long long)cnt->npix[0];
+  const bool full = n > 0 && px == n_px;
+  if (i_n >= 0) out[i_n] = n;
+  if (i_px >= 0) out[i_px] = full ? 0 : px;
+  if (i_h0 >= 0) out[i_h0] = full ? 0 : cnt->ov_hits[0];
+  if (i_h1 >= 0) out[i_h1] = full ? 0 : cnt->ov_hits[1];
+  if (i_h2 >= 0) out[i_h2] = full ? 0 : cnt->ov_hits[2];
+}
+
+// One labelling of the pixels selected by `sel` in `bits` (8-connected) + up to three colocalisation tests.
+static int ov_query(ecseg_ctx* ctx, const uint8_t* bits, const uint8_t* other, int mode, int sel, int h, int w, int s0, int s1,
+                    int s2, int64_t* out, int i_n, int i_px, int i_h0, int i_h1, int i_h2, cudaStream_t st) {
+  const int n_px = h * w;
+  ECSEG_TRY(ccl_run(ctx, bits, h, w, mode, sel, /*conn8=*/1, 0, st));
+  if (s0 >= 0 || s1 >= 0 || s2 >= 0) {
+    k_ov_flag<<<cdiv(n_px, 256), 256, 0, st>>>(other, n_px, ctx->L, ctx->flag, s0, s1, s2);
+    ECSEG_CHECK_LAUNCH();
+    k_ov_count_hits<<<cdiv(n_px, 256), 256, 0, st>>>(n_px, ctx->L, ctx->flag, ctx->counters);
+    ECSEG_CHECK_LAUNCH();
+  }
+  k_ov_finish<<<1, 32, 0, st>>>(ctx->counters, (long long)n_px, out, i_n, i_px, i_h0, i_h1, i_h2);
+  ECSEG_CHECK_LAUNCH();
+  return ECSEG_OK;
+}
+
+int pp_overlay_counts(ecseg_ctx* ctx, const void* d_img, int h, int w, int ch, int bps, const uint8_t* d_labels, int sens,
+                      uint8_t* d_red_inv, uint8_t* d_green_inv, int64_t* d_out, cudaStream_t st) {
+  if (!d_img || !d_labels || !d_out || ch < 3 || (bps != 1 && bps != 2) || sens < 0 || sens > 255) {
+    ctx->err = "ecseg_overlay_counts: needs an RGB(A) image, 1 or 2 bytes per sample, sensitivity in [0, 255]";
+    return ECSEG_E_INVALID;
+  }
+  const int n_px = h * w;
+  uint8_t* bits = ctx->tmp_a;
+  const int blocks = min(cdiv(n_px, 256 * 4), 148 * 8);
+  if (bps == 1) k_ov_bits<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t*)d_img, n_px, ch, d_labels, sens, bits, d_red_inv, d_green_inv);
+  else k_ov_bits<uint16_t><<<blocks, 256, 0, st>>>((const uint16_t*)d_img, n_px, ch, d_labels, sens, bits, d_red_inv, d_green_inv);
+  ECSEG_CHECK_LAUNCH();
+  // remove_small_objects(fish, 20): 4-connected components with area (image_tools.py:104), both probes
+  for (int probe = 0; probe < 2; ++probe) {
+    ECSEG_TRY(ccl_run(ctx, bits, h, w, KEY_BITS, OV_SEL(probe ? OV_FISH2 : OV_FISH, 0), /*conn8=*/0, FIN_AREA, st));
+    k_ov_keep_large<<<cdiv(n_px, 256), 256, 0, st>>>(bits, n_px, ctx->L, ctx->area, kHsrSizeThreshold, probe ? OV_FISH2_L : OV_FISH_L);
+    ECSEG_CHECK_LAUNCH();
+  }
+  // out: [n_ec, px_ec, n_fish, px_fish, n_ec_fish, n_hsr, n_fish2, px_fish2, n_fish_fish2, n_ec_fish2, n_ec_fish_fish2, n_hsr2]
+  // ecDNA components: count_cc(ec), coloc(ec, fish), coloc(ec, fish2), coloc(ec, fish2*fish)   (meta_overlay.py:70,72,80,81)
+  ECSEG_TRY(ov_query(ctx, bits, bits, KEY_BITS, OV_SEL(OV_EC, 0), h, w, OV_SEL(OV_FISH, 0), OV_SEL(OV_FISH2, 0),
+                     OV_SEL(OV_FISH | OV_FISH2, 0), d_out, 0, 1, 4, 9, 10, st));
+  // chromosome components touched by large FISH signal: count_HSR                               (:73,82)
+  ECSEG_TRY(ov_query(ctx, bits, bits, KEY_BITS, OV_SEL(OV_CHROM, 0), h, w, OV_SEL(OV_FISH_L, 0), OV_SEL(OV_FISH2_L, 0), -1,
+                     d_out, -1, -1, 5, 11, -1, st));
+  // fish * ~chrom: count_cc + coloc with fish2 * ~chrom                                         (:71,79)
+  ECSEG_TRY(ov_query(ctx, bits, bits, KEY_BITS, OV_SEL(OV_FISH, OV_CHROM), h, w, OV_SEL(OV_FISH2, OV_CHROM), -1, -1, d_out, 2, 3,
+                     8, -1, -1, st));
+  // fish2 * ~chrom: count_cc                                                                   (:78)
+  ECSEG_TRY(ov_query(ctx, bits, bits, KEY_BITS, OV_SEL(OV_FISH2, OV_CHROM), h, w, -1, -1, -1, d_out, 6, 7, -1, -1, -1, st));
+  return ECSEG_OK;
+}
+
+// image_tools.count_colocalization (image_tools.py:126-134) on two plain masks
+int pp_count_colocalization(ecseg_ctx* ctx, const uint8_t* d_ob1, const uint8_t* d_ob2, int h, int w, int64_t* d_out,
+                            cudaStream_t st) {
+  // selector "any bit set" is not expressible as KEY_BITS: test the three low bits separately is wrong for
+  // general masks, so normalise ob2 into bit 0 of a scratch map first
+  const int n_px = h * w;
+  k_ov_nonzero<<<cdiv(n_px, 256), 256, 0, st>>>(d_ob2, n_px, ctx->tmp_b);
+  ECSEG_CHECK_LAUNCH();
+  return ov_query(ctx, d_ob1, ctx->tmp_b, KEY_NONZERO, 0, h, w, OV_SEL(1, 0), -1, -1, d_out, -1, -1, 0, -1, -1, st);
+}
+
+// skimage.morphology.remove_small_objects on a bool mask (image_tools.py:104): 4-connected, size < min_size dropped
+int pp_remove_small_objects(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w, int min_size, uint8_t* d_out, cudaStream_t st) {
+  const int n_px = h * w;
+  ECSEG_TRY(ccl_run(ctx, d_mask, h, w, KEY_NONZERO, 0, /*conn8=*/0, FIN_AREA, st));
+  ECSEG_CUDA(cudaMemsetAsync(d_out, 0, n_px, st));
+  k_ov_keep_large<<<cdiv(n_px, 256), 256, 0, st>>>(d_out, n_px, ctx->L, ctx->area, min_size, 1);
+  ECSEG_CHECK_LAUNCH();
+  return ECSEG_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

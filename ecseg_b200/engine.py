@@ -180,6 +180,42 @@ class Engine:
         self._chk(self.lib.ecseg_label(self.ctx, m.data_ptr(), h, w, connectivity, out.data_ptr(), self._stream()))
         return out
 
+    # -- meta_overlay ---------------------------------------------------------------------------
+    OVERLAY_OUT = ("n_ecDNA", "px_ecDNA", "n_FISH", "px_FISH", "n_ecDNA_FISH", "n_HSR", "n_FISH2", "px_FISH2",
+                   "n_FISH_FISH2", "n_ecDNA_FISH2", "n_ecDNA_FISH_FISH2", "n_HSR2")
+
+    def overlay_counts(self, img, labels, sensitivity: int, want_planes: bool = False):
+        """Per-image body of meta_overlay (reference src/meta_overlay.py:59-83) on the GPU.
+        Returns the 12 integers of ecseg_overlay_counts as a dict (+ inverted red / green planes)."""
+        a = img if isinstance(img, torch.Tensor) else np.asarray(img)
+        h, w, ch = a.shape
+        bps = 2 if (a.dtype in (np.uint16, torch.int16, torch.uint16)) else 1
+        d = self._dev(a)
+        lab = self._dev(labels, torch.uint8)
+        out = torch.zeros(12, dtype=torch.int64, device=self.device)
+        red = torch.empty((h, w), dtype=torch.uint8, device=self.device) if want_planes else None
+        green = torch.empty_like(red) if want_planes else None
+        self._chk(self.lib.ecseg_overlay_counts(self.ctx, d.data_ptr(), h, w, ch, bps, lab.data_ptr(), int(sensitivity),
+                                                red.data_ptr() if want_planes else None,
+                                                green.data_ptr() if want_planes else None, out.data_ptr(), self._stream()))
+        res = dict(zip(self.OVERLAY_OUT, (int(v) for v in out.cpu().numpy())))
+        return (res, red, green) if want_planes else res
+
+    def count_colocalization(self, ob1, ob2) -> int:
+        a = self._dev(np.asarray(ob1).astype(np.uint8) if not isinstance(ob1, torch.Tensor) else ob1, torch.uint8)
+        b = self._dev(np.asarray(ob2).astype(np.uint8) if not isinstance(ob2, torch.Tensor) else ob2, torch.uint8)
+        h, w = a.shape
+        out = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._chk(self.lib.ecseg_count_colocalization(self.ctx, a.data_ptr(), b.data_ptr(), h, w, out.data_ptr(), self._stream()))
+        return int(out.item())
+
+    def remove_small_objects(self, mask, min_size: int) -> torch.Tensor:
+        m = self._dev(np.asarray(mask).astype(np.uint8) if not isinstance(mask, torch.Tensor) else mask, torch.uint8)
+        h, w = m.shape
+        out = torch.empty_like(m)
+        self._chk(self.lib.ecseg_remove_small_objects(self.ctx, m.data_ptr(), h, w, int(min_size), out.data_ptr(), self._stream()))
+        return out
+
     # -- whole image ----------------------------------------------------------------------------
     def segment_device(self, img: torch.Tensor, h: int, w: int, ch: int, bps: int, faithful_merge=False, out=None):
         """Device-resident path: returns (labels, dapi, n_ec tensor, ec_px tensor) without syncing.

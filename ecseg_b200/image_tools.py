@@ -7,6 +7,9 @@ argument meaning and return types, computed by libecseg_b200 on the GPU.
     patches2im_overlap + img_as_ubyte + argmax     ecseg_stitch_argmax   (stitch_argmax below)
     meta_inference             :15-84              ecseg_postprocess
     count_cc                   :114-119            ecseg_count_cc
+    count_colocalization       :126-134            ecseg_count_colocalization
+    count_HSR                  :103-112            ecseg_remove_small_objects + ecseg_count_colocalization
+    split_FISH_channels        :136-146            (thresholds on the host here; fused in ecseg_overlay_counts)
 """
 from __future__ import annotations
 
@@ -80,3 +83,16 @@ def count_cc(I: np.ndarray):
     """(number of 8-connected components, pixel total) of a boolean mask (reference :114-119)."""
     eng = default_engine(*I.shape)
     return eng.count_cc(np.asarray(I) != 0)
+
+
+def count_colocalization(ob1: np.ndarray, ob2: np.ndarray) -> int:
+    """Number of 8-connected components of ob1 holding at least one pixel of ob2 (reference :126-134)."""
+    eng = default_engine(*ob1.shape)
+    return eng.count_colocalization(np.asarray(ob1) != 0, np.asarray(ob2) != 0)
+
+
+def count_HSR(chrom: np.ndarray, fish: np.ndarray, HSR_SIZE_THRESHOLD: int) -> int:
+    """Chromosome components touched by FISH signal left after remove_small_objects (reference :103-112)."""
+    eng = default_engine(*chrom.shape)
+    big = eng.remove_small_objects(np.asarray(fish) != 0, HSR_SIZE_THRESHOLD)
+    return eng.count_colocalization(eng._dev((np.asarray(chrom) != 0).astype(np.uint8)), big)

@@ -110,8 +110,7 @@ def synth_fish(seed: int, h: int = 2048, w: int = 2048, dtype: str = "u8") -> np
     """RGB image: DAPI in B, green / red FISH spots in G / R (reference image_tools.py:136-146)."""
     rng = _rng(seed + 7919)
     dapi = synth_dapi(seed, h, w)
-    rgb = np.zeros((h, w, 3), np.float32)
-    rgb[..., 2] = dapi
+    planes = [np.zeros((h, w), np.float32), np.zeros((h, w), np.float32), dapi.astype(np.float32)]
     bright = np.argwhere(dapi > 120)
     for ch in (0, 1):
         n = int(rng.integers(20, 120))
@@ -120,8 +119,13 @@ def synth_fish(seed: int, h: int = 2048, w: int = 2048, dtype: str = "u8") -> np
         else:
             pick = np.stack([rng.integers(0, h, n), rng.integers(0, w, n)], 1)
         for (y, x) in pick:
-            cv2.circle(rgb[..., ch], (int(x), int(y)), int(rng.integers(1, 5)), float(rng.integers(100, 256)), -1)
-    out = np.clip(np.rint(rgb), 0, 255).astype(np.uint8)
+            cv2.circle(planes[ch], (int(x), int(y)), int(rng.integers(1, 5)), float(rng.integers(100, 256)), -1)
+        # a few larger signals (HSR-like, survive the 20-px small-object filter) and dim background speckle
+        for (y, x) in pick[: max(1, n // 6)]:
+            cv2.ellipse(planes[ch], (int(x), int(y)), (int(rng.integers(4, 9)), int(rng.integers(2, 5))),
+                        float(rng.integers(0, 180)), 0, 360, float(rng.integers(100, 256)), -1)
+        planes[ch] += rng.integers(0, 60, (h, w)).astype(np.float32)
+    out = np.clip(np.rint(np.stack(planes, -1)), 0, 255).astype(np.uint8)
     if dtype == "u16":
         out = out.astype(np.uint16) * 257
     return out

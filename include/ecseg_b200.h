@@ -108,6 +108,29 @@ int ecseg_merge_comp(ecseg_ctx* ctx, uint8_t* d_labels, int h, int w, int class_
 int ecseg_label(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w, int connectivity, int32_t* d_out,
                 void* stream);
 
+/* ---- meta_overlay ---------------------------------------------------- */
+
+/* Replaces the per-image body of meta_overlay.main (src/meta_overlay.py:59-83): split_FISH_channels
+ * (src/image_tools.py:136-146: u16->u8, red = I[...,0] > s, green = I[...,1] > s), the read_seg masks
+ * (src/utils.py:125-132), the nucleus mask-out, and the nine counts.  d_img: [h,w,ch>=3] interleaved RGB(A);
+ * d_labels: uint8 [h,w] label map of metaseg.  d_red_inv / d_green_inv (nullable): 255 - channel, the planes the
+ * reference writes to red/<name>.png and green/<name>.png.  d_out12 (device int64[12]) =
+ *   [n_ecDNA, px_ecDNA, n_FISH, px_FISH, n_ecDNA_FISH, n_HSR, n_FISH2, px_FISH2, n_FISH_FISH2, n_ecDNA_FISH2,
+ *    n_ecDNA_FISH_FISH2, n_HSR2]   (FISH = green, FISH2 = red; the (n, px) pairs are count_cc tuples). */
+int ecseg_overlay_counts(ecseg_ctx* ctx, const void* d_img, int h, int w, int ch, int bytes_per_sample,
+                         const uint8_t* d_labels, int sensitivity, uint8_t* d_red_inv, uint8_t* d_green_inv, int64_t* d_out12,
+                         void* stream);
+
+/* Replaces image_tools.count_colocalization (src/image_tools.py:126-134): 8-connected components of the
+ * non-zero mask d_ob1 that hold at least one non-zero pixel of d_ob2 -> *d_n (device int64). */
+int ecseg_count_colocalization(ecseg_ctx* ctx, const uint8_t* d_ob1, const uint8_t* d_ob2, int h, int w, int64_t* d_n,
+                               void* stream);
+
+/* Replaces skimage.morphology.remove_small_objects as count_HSR calls it (src/image_tools.py:104): 4-connected
+ * components of the non-zero mask with fewer than min_size pixels are cleared; d_out uint8 [h,w] in {0,1}. */
+int ecseg_remove_small_objects(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w, int min_size, uint8_t* d_out,
+                               void* stream);
+
 /* ---- whole image -------------------------------------------------------------------------- */
 
 /* Replaces utils.meta_segment (src/utils.py:109-120) minus file I/O, plus count_cc(I==3):

@@ -16,6 +16,7 @@ Fixtures (all small, compressed):
   tiling.npz      im2patches_overlap positions + provenance-coded patches2im_overlap canvases
   preprocess.npz  meta_preprocess on u8/u16/gray/RGB/bright-background inputs
   segment.npz     utils.meta_segment end to end with a deterministic fake model (tif on disk)
+  overlay.npz     meta_overlay's per-image counts (count_cc / count_colocalization / count_HSR)
 """
 from __future__ import annotations
 
@@ -85,10 +86,51 @@ def postproc_cases():
     return cases
 
 
+def gen_overlay(it):
+    """meta_overlay per-image body (src/meta_overlay.py:59-83) through the reference's own helpers."""
+    d = {}
+    cases = []
+    for s in range(10):
+        h, w = [(160, 200), (256, 256), (300, 330)][s % 3]
+        I = synth.synth_fish(s, h, w, dtype="u16" if s % 4 == 3 else "u8")
+        seg = synth.synth_label_map(300 + s, h, w)
+        cases.append((I, seg, [85, 10, 200, 0, 255][s % 5]))
+    # quirk cases: everything ecDNA / everything chromosome (np.unique(...)[1:] drops the only component)
+    I = synth.synth_fish(20, 64, 64)
+    cases.append((I, np.full((64, 64), 3, np.uint8), 85))
+    cases.append((I, np.full((64, 64), 2, np.uint8), 20))
+    cases.append((np.full((64, 64, 3), 255, np.uint8), synth.synth_label_map(321, 64, 64), 85))
+    for i, (I, seg, sens) in enumerate(cases):
+        red = it.u16_to_u8(I)[..., 0] > sens
+        green = it.u16_to_u8(I)[..., 1] > sens
+        seg64 = seg.astype(np.int64)
+        nuclei, chrom, ec = seg64 == 1, seg64 == 2, seg64 == 3
+        fish = green * ~nuclei
+        fish2 = red * ~nuclei
+        vals = [it.count_cc(ec), it.count_cc(fish * ~chrom), it.count_colocalization(ec, fish),
+                it.count_HSR(chrom, fish, 20), it.count_cc(fish2 * ~chrom),
+                it.count_colocalization(fish * ~chrom, fish2 * ~chrom), it.count_colocalization(ec, fish2),
+                it.count_colocalization(ec, fish2 * fish), it.count_HSR(chrom, fish2, 20)]
+        flat = []
+        for v in vals:
+            flat.extend([int(x) for x in v] if isinstance(v, tuple) else [int(v)])
+        d[f"img_{i}"] = I
+        d[f"seg_{i}"] = seg.astype(np.uint8)
+        d[f"sens_{i}"] = np.array(sens)
+        # [n_ec, px_ec, n_fish, px_fish, n_ec_fish, n_hsr, n_fish2, px_fish2, n_fish_fish2, n_ec_fish2, n_ec_fish_fish2, n_hsr2]
+        d[f"out_{i}"] = np.array(flat, np.int64)
+    d["n_cases"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(OUT, "overlay.npz"), **d)
+    print("overlay.npz:", len(cases), "cases")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     warnings.simplefilter("ignore")
     it, ut = ref_harness.load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "overlay":
+        gen_overlay(it)
+        return
     nested = lift_nested(it.meta_inference)
     assert set(nested) >= {"merge_comp", "fill_holes", "size_thresh"}, nested.keys()
 
@@ -178,6 +220,8 @@ def main():
     d["names"] = np.array(list(seg_in))
     np.savez_compressed(os.path.join(OUT, "segment.npz"), **d)
     print("segment.npz:", len(seg_in), "images")
+
+    gen_overlay(it)
 
 
 if __name__ == "__main__":

@@ -349,3 +349,75 @@ def overlay_rgba(labels: np.ndarray) -> np.ndarray:
     pal = np.array([(56, 108, 176, 255), (255, 255, 153, 255), (127, 201, 127, 255), (240, 2, 127, 255)],
                    np.uint8)
     return pal[np.clip(labels, 0, 3).astype(np.int64)]
+
+
+# --------------------------------------------------------------------------------------------
+# meta_overlay  (src/meta_overlay.py:14-102, helpers src/image_tools.py:103-146)
+# --------------------------------------------------------------------------------------------
+HSR_SIZE_THRESHOLD = 20    # src/meta_overlay.py:12
+
+
+def split_FISH_channels(I: np.ndarray, sensitivity: int):
+    """src/image_tools.py:136-146 without the file writes: returns (red mask, green mask,
+    inverted red plane, inverted green plane) -- the planes are what the reference writes to
+    red/<name>.png and green/<name>.png.  None for non-RGB input (the reference returns 0)."""
+    if I.ndim < 3:
+        return None
+    I = u16_to_u8(I)
+    r, g = np.uint8(I[..., 0]), np.uint8(I[..., 1])
+    return (r > sensitivity), (g > sensitivity), 255 - r, 255 - g
+
+
+def remove_small_objects(mask: np.ndarray, min_size: int) -> np.ndarray:
+    """skimage.morphology.remove_small_objects on a bool image (call site src/image_tools.py:104):
+    4-connected components (connectivity=1) with fewer than min_size pixels are cleared."""
+    lab, _ = ndi.label(mask, ndi.generate_binary_structure(2, 1))
+    sizes = np.bincount(lab.ravel())
+    out = mask.copy()
+    out[(sizes < min_size)[lab]] = False
+    return out
+
+
+def count_colocalization(ob1: np.ndarray, ob2: np.ndarray) -> int:
+    """src/image_tools.py:126-134 -- 8-connected components of ob1 holding >= 1 pixel of ob2.
+    Quirk kept: np.unique(regs)[1:] drops the smallest label present; with no background pixel in
+    ob1 the single component itself is dropped and the result is 0."""
+    lab, n = _label8(ob1)
+    if n == 0 or np.count_nonzero(lab) == lab.size:
+        return 0
+    hit = np.unique(lab[(lab > 0) & (ob2 != 0)])
+    return int(len(hit))
+
+
+def count_HSR(chrom: np.ndarray, fish: np.ndarray, size_threshold: int = HSR_SIZE_THRESHOLD) -> int:
+    """src/image_tools.py:103-112 -- chromosome components touched by FISH signal that survives
+    remove_small_objects(fish, size_threshold)."""
+    return count_colocalization(chrom, remove_small_objects(fish.astype(bool), size_threshold))
+
+
+OVERLAY_FIELDS = ("num_ecDNA", "num_FISH", "num_FISH2", "num_ecDNA_FISH", "num_ecDNA_FISH2", "num_FISH_FISH2",
+                  "num_ecDNA_FISH_FISH2", "num_HSR2", "num_HSR")
+
+
+def overlay_counts(I: np.ndarray, seg: np.ndarray, sensitivity: int):
+    """The per-image body of meta_overlay.main (src/meta_overlay.py:59-83): dict of the nine CSV
+    cells (count_cc cells are (count, pixel total) tuples, as the reference stores them).
+    first_fish = green, second_fish = red (:52-53).  None for non-RGB input."""
+    sp = split_FISH_channels(I, sensitivity)
+    if sp is None:
+        return None
+    red, green = sp[0], sp[1]
+    nuclei, chrom, ec = (seg == 1), (seg == 2), (seg == 3)
+    fish = green & ~nuclei
+    fish2 = red & ~nuclei
+    return {
+        "num_ecDNA": count_cc(ec),
+        "num_FISH": count_cc(fish & ~chrom),
+        "num_ecDNA_FISH": count_colocalization(ec, fish),
+        "num_HSR": count_HSR(chrom, fish),
+        "num_FISH2": count_cc(fish2 & ~chrom),
+        "num_FISH_FISH2": count_colocalization(fish & ~chrom, fish2 & ~chrom),
+        "num_ecDNA_FISH2": count_colocalization(ec, fish2),
+        "num_ecDNA_FISH_FISH2": count_colocalization(ec, fish2 & fish),
+        "num_HSR2": count_HSR(chrom, fish2),
+    }

@@ -124,3 +124,24 @@ def test_overlay_palette():
     lab = np.array([[0, 1], [2, 3]])
     assert mo.overlay_rgba(lab).tolist() == [[[56, 108, 176, 255], [255, 255, 153, 255]],
                                              [[127, 201, 127, 255], [240, 2, 127, 255]]]
+
+
+OVERLAY_KEYS = ("num_ecDNA", "num_FISH", "num_ecDNA_FISH", "num_HSR", "num_FISH2", "num_FISH_FISH2", "num_ecDNA_FISH2",
+                "num_ecDNA_FISH_FISH2", "num_HSR2")
+
+
+def _flat_overlay(res):
+    out = []
+    for k in OVERLAY_KEYS:
+        v = res[k]
+        out.extend(v if isinstance(v, tuple) else [v])
+    return [int(x) for x in out]
+
+
+def test_meta_overlay_counts(golden):
+    """meta_overlay per-image body (reference src/meta_overlay.py:59-83) incl. the np.unique()[1:] quirk cases."""
+    g = golden("overlay")
+    for i in range(int(g["n_cases"])):
+        res = mo.overlay_counts(g[f"img_{i}"], g[f"seg_{i}"], int(g[f"sens_{i}"]))
+        assert _flat_overlay(res) == [int(v) for v in g[f"out_{i}"]], i
+    assert mo.overlay_counts(g["img_0"][..., 0], g["seg_0"], 85) is None      # non-RGB images are skipped

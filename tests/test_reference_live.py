@@ -54,3 +54,23 @@ def test_preprocess_on_fresh_images(ref):
     for s, kw in [(41, {}), (42, {"invert": True}), (43, {"dtype": "u16"}), (44, {"rgb": True, "invert": True})]:
         img = synth.synth_dapi(s, 270, 290, **kw)
         assert np.array_equal(it.meta_preprocess(img.copy()), mo.meta_preprocess(img.copy()))
+
+
+def test_overlay_helpers_on_fresh_inputs(ref):
+    it, _ = ref
+    for s in range(60, 66):
+        h, w = 140 + 10 * (s % 3), 180
+        I = synth.synth_fish(s, h, w, dtype="u16" if s % 2 else "u8")
+        seg = synth.synth_label_map(400 + s, h, w).astype(np.int64)
+        sens = (85, 30, 180)[s % 3]
+        red = it.u16_to_u8(I)[..., 0] > sens
+        green = it.u16_to_u8(I)[..., 1] > sens
+        nuclei, chrom, ec = seg == 1, seg == 2, seg == 3
+        fish, fish2 = green * ~nuclei, red * ~nuclei
+        got = mo.overlay_counts(I, seg, sens)
+        assert tuple(map(int, it.count_cc(fish * ~chrom))) == got["num_FISH"]
+        assert it.count_colocalization(ec, fish) == got["num_ecDNA_FISH"]
+        assert it.count_colocalization(fish * ~chrom, fish2 * ~chrom) == got["num_FISH_FISH2"]
+        assert it.count_colocalization(ec, fish2 * fish) == got["num_ecDNA_FISH_FISH2"]
+        assert it.count_HSR(chrom, fish, 20) == got["num_HSR"]
+        assert it.count_HSR(chrom, fish2, 20) == got["num_HSR2"]
