@@ -36,7 +36,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;          // warps 0-3: producer / MMA / TMEM alloc / spare, warps 4-11: two epilogue groups
 constexpr int kEpiWarp0 = 4;
 constexpr int kHaloPitch = 18;
 constexpr int kABytes = 18 * 18 * 128;             // bytes one halo load delivers
@@ -46,18 +46,38 @@ constexpr int kPoolStage = 32 * 128;               // pooled staging tile: 32 pi
 constexpr int kMaxBars = 32;
 constexpr int kMaxCout = 1024;
 
-__host__ __device__ constexpr int smem_bytes(int n_tile, int a_stages, int b_stages) {
-  return a_stages * kAStride + b_stages * n_tile * 128 + 2 * kOutStage + 2 * kPoolStage + kMaxCout * 4 +
+// Transposed conv: the 9 taps grouped by the halo view (dy, dx) they read.  acc' = px*2 + py is the accumulator
+// (output parity) a tap feeds; taps of one view sit in consecutive 8 KB slots of one weight stage so that
+// accumulators that are adjacent in TMEM are covered by ONE wider MMA:
+//   view 0 (dy=1,dx=1): taps (ky,kx) = (0,0) (1,0) (0,1) (1,1) -> acc' 0..3  : one N=256 MMA
+//   view 1 (dy=1,dx=0): taps (0,2) (1,2)                       -> acc' 0,1   : one N=128 MMA
+//   view 2 (dy=0,dx=1): taps (2,0) (2,1)                       -> acc' 0,2   : two N=64 MMAs
+//   view 3 (dy=0,dx=0): tap  (2,2)                             -> acc' 0     : one N=64 MMA
+// i.e. 5 reads of a shifted halo view per K step instead of 9 (the N=64 MMA is shared-memory bound on A).
+constexpr int kNumViews = 4;
+__device__ constexpr int kViewDy[kNumViews] = {1, 1, 0, 0};
+__device__ constexpr int kViewDx[kNumViews] = {1, 0, 1, 0};
+__device__ constexpr int kViewTaps[kNumViews] = {4, 2, 2, 1};
+__device__ constexpr int kViewTap[kNumViews][4] = {{0, 3, 1, 4}, {2, 5, 0, 0}, {6, 7, 0, 0}, {8, 0, 0, 0}};
+
+// bytes of one weight stage in ONE CTA: a tap tile (conv) or a view's tap tiles (transposed conv); a CTA pair splits it
+__host__ __device__ constexpr int b_stage_bytes(int n_tile, int nacc, bool pair) {
+  return (nacc == 4 ? 4 * n_tile * 128 : n_tile * 128) / (pair ? 2 : 1);
+}
+__host__ __device__ constexpr int smem_bytes(int n_tile, int nacc, bool pair, int a_stages, int b_stages) {
+  return a_stages * kAStride + b_stages * b_stage_bytes(n_tile, nacc, pair) + 2 * kOutStage + 2 * kPoolStage + kMaxCout * 4 +
          kMaxBars * 8 + 16 + 1024;
 }
 
-template <int N_TILE, int NACC, int CS>
+template <int N_TILE, int NACC, int CS, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__ ConvTcParams p) {
-  constexpr int kBBytes = N_TILE * 128;
+  constexpr int kBBytes = N_TILE * 128;                 // one tap's weight tile
+  constexpr int kBStage = b_stage_bytes(N_TILE, NACC, PAIR);  // conv: one tap; transposed conv: one view (up to 4 taps)
   constexpr int kAccCols = 2 * NACC * N_TILE;
   constexpr int kAccStages = (2 * kAccCols <= 512) ? 2 : 1;
   constexpr int kTmemCols = 512;
   static_assert(kAccCols <= 512, "accumulators exceed TMEM");
+  static_assert(!PAIR || CS == 2, "a CTA pair is a cluster of 2");
 
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms repeat every 1024 B: align the stage area (same offset in every CTA of a cluster)
@@ -65,9 +85,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
   const int AS = p.a_stages, BS = p.b_stages;
   const uint32_t a_base = smem_u32(smem);
   const uint32_t b_base = a_base + AS * kAStride;
-  const uint32_t o_base = b_base + BS * kBBytes;                 // 2 output staging tiles
+  const uint32_t o_base = b_base + BS * kBStage;                 // 2 output staging tiles (one per epilogue group)
   const uint32_t q_base = o_base + 2 * kOutStage;                // 2 pooled staging tiles
-  float* s_bias = reinterpret_cast<float*>(smem + AS * kAStride + BS * kBBytes + 2 * kOutStage + 2 * kPoolStage);
+  float* s_bias = reinterpret_cast<float*>(smem + AS * kAStride + BS * kBStage + 2 * kOutStage + 2 * kPoolStage);
   const uint32_t s_bias_u32 = q_base + 2 * kPoolStage;
   const uint32_t bar_base = s_bias_u32 + kMaxCout * 4;
   auto full_a = [&](int s) { return bar_base + 8u * s; };
@@ -76,7 +96,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
   auto empty_b = [&](int s) { return bar_base + 8u * (2 * AS + BS + s); };
   auto tmem_full = [&](int s) { return bar_base + 8u * (2 * AS + 2 * BS + s); };
   auto tmem_empty = [&](int s) { return bar_base + 8u * (2 * AS + 2 * BS + 2 + s); };
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + AS * kAStride + BS * kBBytes + 2 * kOutStage +
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + AS * kAStride + BS * kBStage + 2 * kOutStage +
                                                         2 * kPoolStage + kMaxCout * 4 + kMaxBars * 8);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
@@ -85,11 +105,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < AS; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
-    for (int s = 0; s < BS; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), CS); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), 128); }
+    for (int s = 0; s < BS; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), PAIR ? 1 : CS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), PAIR ? 512 : 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
-    tmem_alloc(smem_u32(tmem_ptr_smem), kTmemCols);
+    if (PAIR) tmem_alloc_2sm(smem_u32(tmem_ptr_smem), kTmemCols);
+    else tmem_alloc(smem_u32(tmem_ptr_smem), kTmemCols);
   } else if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tm_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tm_b) : "memory");
@@ -129,32 +150,97 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         ok = __all_sync(0xffffffffu, mbar_wait(empty_a(sa), pa ^ 1, p.device_error, 1));
         if (!ok) break;
         if (leader) {
-          mbar_expect_tx(full_a(sa), kABytes);
-          tma_load_4d(a_base + sa * kAStride, &p.tm_a, full_a(sa), ch * 64, x0 - 1, y0 - 1, img);
+          if (PAIR) {   // both CTAs' halos complete on the leader CTA's barrier
+            if (rank == 0) mbar_expect_tx(full_a(sa), 2 * kABytes);
+            tma_load_4d_2sm(a_base + sa * kAStride, &p.tm_a, full_a(sa), ch * 64, x0 - 1, y0 - 1, img);
+          } else {
+            mbar_expect_tx(full_a(sa), kABytes);
+            tma_load_4d(a_base + sa * kAStride, &p.tm_a, full_a(sa), ch * 64, x0 - 1, y0 - 1, img);
+          }
         }
         if (++sa == AS) { sa = 0; pa ^= 1; }
-        for (int t = 0; t < 9; ++t) {
-          ok = __all_sync(0xffffffffu, mbar_wait(empty_b(sb), pb ^ 1, p.device_error, 2));
-          if (!ok) break;
-          if (leader) {
-            mbar_expect_tx(full_b(sb), kBBytes);
-            const int row = t * p.cout_rows + nch * N_TILE;
-            if (CS == 1) {
-              tma_load_2d(b_base + sb * kBBytes, &p.tm_b, full_b(sb), ch * 64, row);
-            } else {
-              tma_load_2d_mc(b_base + sb * kBBytes + rank * (kBBytes / CS), &p.tm_b, full_b(sb), ch * 64,
-                             row + (int)rank * (N_TILE / CS), (uint16_t)((1u << CS) - 1));
+        if (NACC == 1) {
+          for (int t = 0; t < 9; ++t) {
+            ok = __all_sync(0xffffffffu, mbar_wait(empty_b(sb), pb ^ 1, p.device_error, 2));
+            if (!ok) break;
+            if (leader) {
+              const int row = t * p.cout_rows + nch * N_TILE;
+              if (PAIR) {   // each CTA keeps its half of the tile (rows = output channels) in its own shared memory
+                if (rank == 0) mbar_expect_tx(full_b(sb), kBBytes);
+                tma_load_2d_2sm(b_base + sb * kBStage, &p.tm_b, full_b(sb), ch * 64, row + (int)rank * (N_TILE / 2));
+              } else if (CS == 1) {
+                mbar_expect_tx(full_b(sb), kBBytes);
+                tma_load_2d(b_base + sb * kBStage, &p.tm_b, full_b(sb), ch * 64, row);
+              } else {
+                mbar_expect_tx(full_b(sb), kBBytes);
+                tma_load_2d_mc(b_base + sb * kBStage + rank * (kBBytes / CS), &p.tm_b, full_b(sb), ch * 64,
+                               row + (int)rank * (N_TILE / CS), (uint16_t)((1u << CS) - 1));
+              }
             }
+            if (++sb == BS) { sb = 0; pb ^= 1; }
           }
-          if (++sb == BS) { sb = 0; pb ^= 1; }
+        } else {
+#pragma unroll
+          for (int v = 0; v < kNumViews; ++v) {
+            ok = __all_sync(0xffffffffu, mbar_wait(empty_b(sb), pb ^ 1, p.device_error, 2));
+            if (!ok) break;
+            if (leader && PAIR) {
+              // the pair's MMA splits B along N between the CTAs: for the merged views (N = 256 / 128) that is a
+              // split by TAP (accumulator), for the N = 64 MMAs a split by output-channel half.  tm_b boxes are 32 rows.
+              if (rank == 0) mbar_expect_tx(full_b(sb), kViewTaps[v] * kBBytes);
+              const uint32_t dst = b_base + sb * kBStage;
+              const uint32_t bar = full_b(sb);
+              const int r32 = (int)rank * 32;
+              auto tap_row = [&](int j) { return kViewTap[v][j] * p.cout_rows + nch * N_TILE; };
+              if (v == 0) {          // taps 2r, 2r+1, all 64 rows each
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                  for (int hh = 0; hh < 2; ++hh)
+                    tma_load_2d_2sm(dst + j * kBBytes + hh * (kBBytes / 2), &p.tm_b, bar, ch * 64, tap_row(2 * (int)rank + j) + hh * 32);
+              } else if (v == 1) {   // tap r, all 64 rows
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh)
+                  tma_load_2d_2sm(dst + hh * (kBBytes / 2), &p.tm_b, bar, ch * 64, tap_row((int)rank) + hh * 32);
+              } else if (v == 2) {   // both taps, rows [32r, 32r+32)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) tma_load_2d_2sm(dst + j * (kBBytes / 2), &p.tm_b, bar, ch * 64, tap_row(j) + r32);
+              } else {
+                tma_load_2d_2sm(dst, &p.tm_b, bar, ch * 64, tap_row(0) + r32);
+              }
+            } else if (leader) {
+              mbar_expect_tx(full_b(sb), kViewTaps[v] * kBBytes);
+#pragma unroll
+              for (int j = 0; j < kViewTaps[v]; ++j) {
+                const int row = kViewTap[v][j] * p.cout_rows + nch * N_TILE;
+                const uint32_t dst = b_base + sb * kBStage + j * kBBytes;
+                if (CS == 1) tma_load_2d(dst, &p.tm_b, full_b(sb), ch * 64, row);
+                else tma_load_2d_mc(dst + rank * (kBBytes / CS), &p.tm_b, full_b(sb), ch * 64, row + (int)rank * (N_TILE / CS),
+                                    (uint16_t)((1u << CS) - 1));
+              }
+            }
+            if (++sb == BS) { sb = 0; pb ^= 1; }
+          }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && (!PAIR || rank == 0)) {
+    // ===================== MMA issuer (the leader CTA's for a pair) =====================
     const bool leader = elect_one();
-    const uint32_t idesc = make_idesc(128, N_TILE, p.is_bf16);
+    constexpr int kM = PAIR ? 256 : 128;
+    const uint32_t idesc = make_idesc(kM, N_TILE, p.is_bf16);
     const uint32_t a_hi = sdesc_hi(kHaloPitch * 128), b_hi = sdesc_hi(1024);
+    auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t accumulate) {
+      if (PAIR) umma_f16_2sm(d, ad, bd, id, accumulate);
+      else umma_f16(d, ad, bd, id, accumulate);
+    };
+    // arrival (once the MMAs issued so far retire) on a barrier; barriers a pair shares, and the weight barriers of a
+    // multicast cluster, are signalled in every CTA of the cluster
+    auto commit_all = [&](uint32_t bar, bool local_only = false) {
+      if (PAIR) umma_commit_2sm(bar, (uint16_t)3);
+      else if (CS == 1 || local_only) umma_commit(bar);
+      else umma_commit_mc(bar, (uint16_t)((1u << CS) - 1));
+    };
     int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
     bool ok = true;
     for (int it = cluster_id; it < n_items && ok; it += n_clusters) {
@@ -162,55 +248,92 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
       if (!ok) break;
       tc_fence_after();
       const uint32_t d0 = tmem_base + (uint32_t)(as * kAccCols);
-      uint32_t started = 0;
       for (int ch = 0; ch < p.cin_chunks && ok; ++ch) {
         ok = __all_sync(0xffffffffu, mbar_wait(full_a(sa), pa, p.device_error, 4));
         if (!ok) break;
         const uint32_t a_stage = a_base + sa * kAStride;
+        if (NACC == 1) {
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          ok = __all_sync(0xffffffffu, mbar_wait(full_b(sb), pb, p.device_error, 5));
-          if (!ok) break;
-          tc_fence_after();
-          const uint32_t b_lo = sdesc_lo(b_base + sb * kBBytes);
-          const uint32_t a_lo = sdesc_lo(a_stage + (uint32_t)(((int)p.tap_dy[t] * kHaloPitch + (int)p.tap_dx[t]) * 128));
-          const int acc = NACC > 1 ? (int)p.tap_acc[t] : 0;
-          const uint32_t d = d0 + (uint32_t)(acc * 2 * N_TILE);
-          const uint32_t first = (started >> acc) & 1u;
-          started |= 1u << acc;
-          if (leader) {
+          for (int t = 0; t < 9; ++t) {
+            ok = __all_sync(0xffffffffu, mbar_wait(full_b(sb), pb, p.device_error, 5));
+            if (!ok) break;
+            tc_fence_after();
+            const uint32_t b_lo = sdesc_lo(b_base + sb * kBStage);
+            const uint32_t a_lo = sdesc_lo(a_stage + (uint32_t)(((int)p.tap_dy[t] * kHaloPitch + (int)p.tap_dx[t]) * 128));
+            const uint32_t first = (ch > 0 || t > 0) ? 1u : 0u;
+            if (leader) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+              for (int k = 0; k < 4; ++k) {
 #pragma unroll
-              for (int half = 0; half < 2; ++half)
-                umma_f16(d + half * N_TILE, sdesc_join(a_lo + half * 64 + k * 2, a_hi), sdesc_join(b_lo + k * 2, b_hi),
-                         idesc, k > 0 ? 1u : first);
+                for (int half = 0; half < 2; ++half)
+                  mma(d0 + half * N_TILE, sdesc_join(a_lo + half * 64 + k * 2, a_hi), sdesc_join(b_lo + k * 2, b_hi),
+                      idesc, k > 0 ? 1u : first);
+              }
+              // weight stage reusable (in every CTA of the cluster) once these MMAs retire
+              commit_all(empty_b(sb));
             }
-            // weight stage reusable (in every CTA of the cluster) once these MMAs retire
-            if (CS == 1) umma_commit(empty_b(sb));
-            else umma_commit_mc(empty_b(sb), (uint16_t)((1u << CS) - 1));
+            __syncwarp();
+            if (++sb == BS) { sb = 0; pb ^= 1; }
           }
-          __syncwarp();
-          if (++sb == BS) { sb = 0; pb ^= 1; }
+        } else {
+          // transposed conv: TMEM columns [half][acc'][N_TILE]; one weight stage per halo view
+          const uint32_t idesc4 = make_idesc(kM, 4 * N_TILE, p.is_bf16), idesc2 = make_idesc(kM, 2 * N_TILE, p.is_bf16);
+#pragma unroll
+          for (int v = 0; v < kNumViews; ++v) {
+            ok = __all_sync(0xffffffffu, mbar_wait(full_b(sb), pb, p.device_error, 5));
+            if (!ok) break;
+            tc_fence_after();
+            const uint32_t b_lo = sdesc_lo(b_base + sb * kBStage);
+            const uint32_t a_lo = sdesc_lo(a_stage + (uint32_t)((kViewDy[v] * kHaloPitch + kViewDx[v]) * 128));
+            if (leader) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                  const uint32_t d = d0 + half * (4 * N_TILE);
+                  const uint64_t ad = sdesc_join(a_lo + half * 64 + k * 2, a_hi);
+                  if (v == 0) {
+                    mma(d, ad, sdesc_join(b_lo + k * 2, b_hi), idesc4, (ch > 0 || k > 0) ? 1u : 0u);
+                  } else if (v == 1) {
+                    mma(d, ad, sdesc_join(b_lo + k * 2, b_hi), idesc2, 1u);
+                  } else if (v == 2) {   // second tap's tile: one tap slot further (half a slot per CTA of a pair)
+                    mma(d, ad, sdesc_join(b_lo + k * 2, b_hi), idesc, 1u);
+                    mma(d + 2 * N_TILE, ad, sdesc_join(b_lo + ((kBBytes / (PAIR ? 2 : 1)) >> 4) + k * 2, b_hi), idesc, 1u);
+                  } else {
+                    mma(d, ad, sdesc_join(b_lo + k * 2, b_hi), idesc, 1u);
+                  }
+                }
+              }
+              commit_all(empty_b(sb));
+            }
+            __syncwarp();
+            if (++sb == BS) { sb = 0; pb ^= 1; }
+          }
         }
-        if (leader) umma_commit(empty_a(sa));     // halo stage reusable
+        if (leader) commit_all(empty_a(sa), /*local_only=*/true);     // halo stage reusable
         __syncwarp();
         if (++sa == AS) { sa = 0; pa ^= 1; }
       }
-      if (leader) umma_commit(tmem_full(as));     // accumulators complete -> epilogue
+      if (leader) commit_all(tmem_full(as), /*local_only=*/true);     // accumulators complete -> epilogue
       __syncwarp();
       if (++as == kAccStages) { as = 0; pacc ^= 1; }
     }
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue =====================
+    // Two epilogue groups of 4 warps (one warp per TMEM lane quarter each) alternate over the
+    // (accumulator, half, 64-channel slab) units of an item; each group owns a staging tile, a pair of
+    // named barriers and its own bulk-store group accounting.
+    const int eg = (warp - kEpiWarp0) >> 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;            // accumulator row = pixel of the 16x8 half block = staging row
     const int r = m >> 3, c = m & 7;
-    const bool e0 = threadIdx.x == kEpiWarp0 * 32;
+    const bool e0 = threadIdx.x == (kEpiWarp0 + 4 * eg) * 32;
     const bool pool_lane = (lane & 9) == 0;                 // even row, even column of the half block
     const int pm = (r >> 1) * 4 + (c >> 1);                 // pooled staging row
+    const uint32_t so = o_base + eg * kOutStage + (uint32_t)m * 128u;
+    const uint32_t sq = q_base + eg * kPoolStage + (uint32_t)pm * 128u;
+    const int bar_a = 1 + eg, bar_b = 3 + eg;
     int as = 0, pacc = 0;
-    uint32_t sidx = 0;
     bool ok = true;
     for (int it = cluster_id; it < n_items && ok; it += n_clusters) {
       const int mg = it % n_mgroups, nch = it / n_mgroups;
@@ -223,23 +346,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
       if (!ok) break;
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccCols);
+      int unit = 0;
 #pragma unroll 1
       for (int acc = 0; acc < NACC; ++acc) {
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
 #pragma unroll 1
           for (int sl = 0; sl < N_TILE / 64; ++sl) {
-            const uint32_t buf = sidx & 1u;
-            ++sidx;
-            if (e0) bulk_wait_read<1>();          // the store that last read this staging buffer is done
-            named_bar_sync(1, 128);
-            const uint32_t so = o_base + buf * kOutStage + (uint32_t)m * 128u;
-            const uint32_t sq = q_base + buf * kPoolStage + (uint32_t)pm * 128u;
+            if (((unit++) & 1) != eg) continue;
+            if (e0) bulk_wait_read<0>();          // the store that last read this group's staging tile is done
+            named_bar_sync(bar_a, 128);
             const uint32_t bs = s_bias_u32 + (uint32_t)(nch * N_TILE + sl * 64) * 4u;
+            const uint32_t tcol = NACC == 4 ? (uint32_t)(half * (4 * N_TILE) + acc * N_TILE) : (uint32_t)(half * N_TILE + sl * 64);
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
               uint32_t v[32];
-              tmem_ld32(t0 + (uint32_t)((acc * 2 + half) * N_TILE + sl * 64 + cc * 32), v);
+              tmem_ld32(t0 + tcol + cc * 32, v);
               tmem_ld_wait();
               float f[32];
 #pragma unroll
@@ -279,13 +401,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
               }
             }
             fence_async_smem();
-            named_bar_sync(2, 128);
+            named_bar_sync(bar_b, 128);
             if (e0) {
               if (!ghost) {
                 const int ch0 = nch * N_TILE + sl * 64;
-                tma_store_4d(&p.tm_out[acc], o_base + buf * kOutStage, p.out_choff + ch0, x0 + half * 8, y0, img);
+                // transposed conv: accumulator acc' = px*2 + py -> tensor map of output parity py*2 + px
+                const int par = NACC == 4 ? ((acc & 1) * 2 + (acc >> 1)) : 0;
+                tma_store_4d(&p.tm_out[par], o_base + eg * kOutStage, p.out_choff + ch0, x0 + half * 8, y0, img);
                 if (NACC == 1 && p.has_pool)
-                  tma_store_4d(&p.tm_pool, q_base + buf * kPoolStage, ch0, (x0 >> 1) + half * 4, y0 >> 1, img);
+                  tma_store_4d(&p.tm_pool, q_base + eg * kPoolStage, ch0, (x0 >> 1) + half * 4, y0 >> 1, img);
               }
               bulk_commit();
             }
@@ -293,7 +417,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         }
       }
       tc_fence_before();
-      mbar_arrive(tmem_empty(as));
+      if (PAIR) mbar_arrive_cluster(tmem_empty(as), 0);   // the leader's MMA warp waits for both CTAs' epilogues
+      else mbar_arrive(tmem_empty(as));
       if (++as == kAccStages) { as = 0; pacc ^= 1; }
     }
     if (e0) bulk_wait<0>();
@@ -304,20 +429,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
   if (CS > 1) cluster_sync_all();     // no CTA leaves while a peer may still multicast into it / signal it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
-template <int N_TILE, int NACC, int CS>
+template <int N_TILE, int NACC, int CS, bool PAIR>
 int launch_cfg(ecseg_ctx* ctx, ConvTcParams& p, cudaStream_t st) {
-  auto kern = k_conv_tc<N_TILE, NACC, CS>;
+  auto kern = k_conv_tc<N_TILE, NACC, CS, PAIR>;
   // pipeline depths: halo stages first (each covers 9 taps of MMA work), the rest goes to weight stages
   const int budget = 227 * 1024;
-  p.a_stages = (N_TILE == 64) ? 3 : 2;
-  p.b_stages = (budget - smem_bytes(N_TILE, p.a_stages, 0)) / (N_TILE * 128);
+  p.a_stages = (N_TILE == 64 && NACC == 1) ? 3 : 2;
+  p.b_stages = (budget - smem_bytes(N_TILE, NACC, PAIR, p.a_stages, 0)) / b_stage_bytes(N_TILE, NACC, PAIR);
   if (p.b_stages > 8) p.b_stages = 8;
   if (p.b_stages < 2 || 2 * p.a_stages + 2 * p.b_stages + 4 > kMaxBars) { ctx->err = "conv_tc: bad pipeline configuration"; return ECSEG_E_INVALID; }
-  const int smem = smem_bytes(N_TILE, p.a_stages, p.b_stages);
+  const int smem = smem_bytes(N_TILE, NACC, PAIR, p.a_stages, p.b_stages);
   static bool attr_done = false;
   if (!attr_done) {
     ECSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
@@ -343,12 +469,12 @@ int launch_cfg(ecseg_ctx* ctx, ConvTcParams& p, cudaStream_t st) {
   return ECSEG_OK;
 }
 
-template <int NACC, int CS>
+template <int NACC, int CS, bool PAIR>
 int launch_n(ecseg_ctx* ctx, ConvTcParams& p, int n_tile, cudaStream_t st) {
   switch (n_tile) {
-    case 64: return launch_cfg<64, NACC, CS>(ctx, p, st);
-    case 128: if (NACC == 1) return launch_cfg<128, 1, CS>(ctx, p, st); break;
-    case 256: if (NACC == 1) return launch_cfg<256, 1, CS>(ctx, p, st); break;
+    case 64: return launch_cfg<64, NACC, CS, PAIR>(ctx, p, st);
+    case 128: if (NACC == 1) return launch_cfg<128, 1, CS, PAIR>(ctx, p, st); break;
+    case 256: if (NACC == 1) return launch_cfg<256, 1, CS, PAIR>(ctx, p, st); break;
   }
   ctx->err = "conv_tc: unsupported N_TILE for this layer kind";
   return ECSEG_E_INVALID;
@@ -361,8 +487,15 @@ int conv_tc_launch(ecseg_ctx* ctx, ConvTcParams& p, int n_tile, int cluster, cud
     ctx->err = "conv_tc: H, W must be multiples of 16, Cin a multiple of 64, Cout <= 1024";
     return ECSEG_E_INVALID;
   }
-  if (p.n_acc == 1) return cluster == 2 ? launch_n<1, 2>(ctx, p, n_tile, st) : launch_n<1, 1>(ctx, p, n_tile, st);
-  if (p.n_acc == 4) return cluster == 2 ? launch_n<4, 2>(ctx, p, n_tile, st) : launch_n<4, 1>(ctx, p, n_tile, st);
+  // cluster: 1 = single CTAs, 2 = CTA clusters sharing weight tiles by TMA multicast, 3 = CTA pairs (cta_group::2 MMA)
+  if (p.n_acc == 1) {
+    if (cluster == 3) return launch_n<1, 2, true>(ctx, p, n_tile, st);
+    return cluster == 2 ? launch_n<1, 2, false>(ctx, p, n_tile, st) : launch_n<1, 1, false>(ctx, p, n_tile, st);
+  }
+  if (p.n_acc == 4) {
+    if (cluster == 3) return launch_n<4, 2, true>(ctx, p, n_tile, st);
+    return cluster == 2 ? launch_n<4, 2, false>(ctx, p, n_tile, st) : launch_n<4, 1, false>(ctx, p, n_tile, st);
+  }
   ctx->err = "conv_tc: n_acc must be 1 or 4";
   return ECSEG_E_INVALID;
 }

@@ -62,7 +62,7 @@ struct UNet {
   int cout_rows[23] = {};
   float* debug_dump = nullptr;
   // tcgen05 knobs (ECSEG_TC_CLUSTER / ECSEG_TC_NTILE_MAX env overrides)
-  int tc_cluster = 2, tc_ntile_max = 256;
+  int tc_cluster = 0, tc_ntile_max = 0;   // 0 = per-layer table
   int stop_after = -1;   // debug: stop the forward after this layer
 };
 
@@ -349,7 +349,7 @@ static void fill_taps(P& p, bool convT) {
 // ------------------------------------------------------------------------------------------------
 int unet_create(ecseg_ctx* ctx) {
   ctx->net = new UNet();
-  if (const char* e = getenv("ECSEG_TC_CLUSTER")) ctx->net->tc_cluster = atoi(e) == 1 ? 1 : 2;
+  if (const char* e = getenv("ECSEG_TC_CLUSTER")) { const int v = atoi(e); if (v >= 1 && v <= 3) ctx->net->tc_cluster = v; }
   if (const char* e = getenv("ECSEG_TC_NTILE_MAX")) ctx->net->tc_ntile_max = atoi(e);
   return ECSEG_OK;
 }
@@ -539,16 +539,24 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   const int out_hw = kTile >> l.level;
   const int in_hw = l.convT ? out_hw / 2 : out_hw;
   const int rows = net->cout_rows[li];
-  // N tile: 256 halves the weight re-fetch per MMA but uses all of TMEM (epilogue not overlapped) and gives
-  // coarser work items; 128 double-buffers the accumulators.  Measured per layer (profiles/r01_launches_v4*.txt):
-  // 128 wins for the short-K / many-block layers of levels 2-3, 256 for level 4 and the 512-channel concat conv.
-  int n_tile = l.convT ? 64 : (rows < 256 ? rows : 256);
-  if (!l.convT && rows >= 256 && (li == 4 || li == 5 || li == 6 || li == 7 || li == 15)) n_tile = 128;
-  if (n_tile > net->tc_ntile_max) n_tile = net->tc_ntile_max;
-  const int cs = net->tc_cluster;
+  // Per-layer kernel variant, measured per layer (profiles/r01_launches_*.txt):
+  //  * CTA pairs (cta_group::2 MMA, "cluster 3") cut the shared-memory operand traffic per MMA (each CTA reads its
+  //    own A rows and only half of B) and win wherever an item has a long K loop;
+  //  * layers whose items are one 64-channel chunk long (conv1-2, conv2-1, up1) lose more to the pair's cross-CTA
+  //    handshakes than they gain and stay on the multicast cluster ("cluster 2");
+  //  * N tile 128 double-buffers the accumulators in TMEM (epilogue overlapped) and gives finer work items; 256
+  //    halves the weight re-fetch and wins only for the 16x16 level.
+  int n_tile = l.convT ? 64 : (rows < 128 ? rows : 128);
+  int cs = 3;
+  if (li == 8 || li == 9) n_tile = 256;             // conv5-1, conv5-2
+  if (li == 1 || li == 2 || li == 19) cs = 2;       // conv1-2, conv2-1, up1
+  if (net->tc_ntile_max > 0 && !l.convT) n_tile = rows < net->tc_ntile_max ? rows : net->tc_ntile_max;   // debug override
+  if (net->tc_cluster > 0) cs = net->tc_cluster;                                                      // debug override
   const size_t pin = kBufs[wr.in].ch, pout = kBufs[wr.out].ch;
   ECSEG_TRY(make_tm_nhwc(ctx, &p.tm_a, net->buf[wr.in], l.cin, in_hw, in_hw, NT, pin, pin * in_hw, pin * in_hw * in_hw, 18, 18, bf16));
-  ECSEG_TRY(make_tm_wgt(ctx, &p.tm_b, net->w[li], l.cin, 9 * rows, n_tile / cs, bf16));
+  // weight boxes: a whole tap tile, or the half a CTA of a cluster / pair fetches (32-row boxes for the pair's transposed conv)
+  const int box_rows = cs == 1 ? n_tile : (cs == 3 && l.convT ? 32 : n_tile / 2);
+  ECSEG_TRY(make_tm_wgt(ctx, &p.tm_b, net->w[li], l.cin, 9 * rows, box_rows, bf16));
   const size_t esz = 2;
   if (!l.convT) {
     p.n_acc = 1;
@@ -638,8 +646,8 @@ int unet_set_debug(ecseg_ctx* ctx, int stop_after, int tc_cluster, int tc_ntile_
   UNet* net = ctx->net;
   if (!net) return ECSEG_E_STATE;
   net->stop_after = stop_after;
-  if (tc_cluster == 1 || tc_cluster == 2) net->tc_cluster = tc_cluster;
-  if (tc_ntile_max == 64 || tc_ntile_max == 128 || tc_ntile_max == 256) net->tc_ntile_max = tc_ntile_max;
+  if (tc_cluster >= 0 && tc_cluster <= 3) net->tc_cluster = tc_cluster;
+  if (tc_ntile_max == 0 || tc_ntile_max == 64 || tc_ntile_max == 128 || tc_ntile_max == 256) net->tc_ntile_max = tc_ntile_max;
   return ECSEG_OK;
 }
 

@@ -85,7 +85,9 @@ class Engine:
                                               PRECISIONS[precision]))
         self.precision = precision
 
-    def debug_set(self, stop_after=-1, tc_cluster=0, tc_ntile_max=0):
+    def debug_set(self, stop_after=-1, tc_cluster=-1, tc_ntile_max=-1):
+        """tc_cluster: 0 per-layer table | 1 single CTAs | 2 multicast clusters | 3 CTA pairs; tc_ntile_max: 0 table |
+        64 | 128 | 256; -1 leaves a setting unchanged."""
         self._chk(self.lib.ecseg_debug_set(self.ctx, stop_after, tc_cluster, tc_ntile_max))
 
     def device_error(self) -> int:

@@ -161,9 +161,10 @@ int ecseg_segment_image_host_wait(ecseg_ctx* ctx, int32_t* n_ec, int64_t* ec_px)
  * [n, H_l, W_l, C_l] (layer index per ecseg_b200.spec.UNET_LAYERS). */
 int ecseg_debug_layer_output(ecseg_ctx* ctx, int layer, int n, float* d_out, void* stream);
 
-/* Debug knobs: stop the U-Net forward after `stop_after_layer` (-1 = run everything) and select the
- * tcgen05 kernel variant (cluster size 1|2 = weight-tile multicast off|on, max N tile 64|128|256);
- * values outside those sets leave the setting unchanged. */
+/* Debug knobs: stop the U-Net forward after `stop_after_layer` (-1 = run everything) and force one tcgen05
+ * kernel variant for every layer: tc_cluster 1 = single CTAs, 2 = CTA clusters sharing weight tiles by TMA
+ * multicast, 3 = CTA pairs (cta_group::2 MMA), 0 = the per-layer table (default); tc_ntile_max 64|128|256, 0 = table.
+ * Any other value (e.g. -1) leaves that setting unchanged. */
 int ecseg_debug_set(ecseg_ctx* ctx, int stop_after_layer, int tc_cluster, int tc_ntile_max);
 
 /* Synchronise and read the device-side pipeline watchdog flag (0 = healthy). */

@@ -97,9 +97,10 @@ def main():
     say(f"fp32 logits max_rel={mx:.3e} mean_rel={mean:.3e} scale={scale:.3g}")
 
     # ---- tcgen05 variants: cluster size (weight multicast) x max N tile ----
-    variants = [("fp16", 1, 256), ("fp16", 2, 256), ("fp16", 2, 128), ("fp16", 2, 64), ("bf16", 2, 256)]
+    variants = [("fp16", 1, 256), ("fp16", 2, 256), ("fp16", 2, 128), ("fp16", 2, 64), ("fp16", 3, 256), ("fp16", 3, 128),
+                ("fp16", 3, 64), ("bf16", 3, 256)]
     if os.environ.get("PROBE_QUICK"):
-        variants = [("fp16", 1, 256), ("fp16", 2, 256)]
+        variants = [("fp16", 2, 256), ("fp16", 3, 256)]
     for prec, cs, ntile in variants:
         eng.load_weights(w, prec)
         if True:
