@@ -42,6 +42,19 @@ SIGNATURES = {
     "ecseg_segment_image_host_async": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                                c_int, c_void_p]),
     "ecseg_segment_image_host_wait": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int64)]),
+    "ecseg_artifact_sizes": (c_int, [c_int, c_int, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t)]),
+    "ecseg_overlay_png": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, POINTER(c_size_t), c_void_p]),
+    "ecseg_labels_npy": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, POINTER(c_size_t), c_void_p]),
+    "ecseg_gray_tiff": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, POINTER(c_size_t), c_void_p]),
+    "ecseg_segment_image_files_async": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                                c_void_p, c_size_t, c_void_p, c_int, c_void_p]),
+    "ecseg_segment_image_files_wait": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int64), POINTER(c_size_t)]),
+    "ecseg_tiff_read": (c_int, [c_char_p, c_void_p, c_size_t, POINTER(c_int), POINTER(c_int), POINTER(c_int),
+                                POINTER(c_int)]),
+    "ecseg_png_wrap": (c_size_t, [c_void_p, c_size_t, c_int, c_int]),
+    "ecseg_npy_header": (c_size_t, [c_void_p, c_size_t, c_int, c_int]),
+    "ecseg_tiff_header": (c_size_t, [c_void_p, c_int, c_int]),
+    "ecseg_crc32": (ctypes.c_uint32, [ctypes.c_uint32, c_void_p, c_size_t]),
     "ecseg_debug_layer_output": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ecseg_debug_set": (c_int, [c_void_p, c_int, c_int, c_int]),
     "ecseg_device_error": (c_int, [c_void_p, POINTER(c_int)]),

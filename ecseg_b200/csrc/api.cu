@@ -1,8 +1,10 @@
 // C ABI of libecseg_b200.so (include/ecseg_b200.h): context lifetime and the entry points the
 // reference-facing Python shim binds.  No exceptions cross this boundary.
+#include <algorithm>
 #include <cstring>
 #include <new>
 
+#include "artifacts_host.h"
 #include "common.cuh"
 
 namespace ecseg {
@@ -68,6 +70,7 @@ void ecseg_ctx_destroy(ecseg_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   unet_destroy(ctx);
+  art_free_workspace(ctx);
   void* ptrs[] = {ctx->L, ctx->area, ctx->sum_y, ctx->sum_x, ctx->flag, ctx->tmp_a, ctx->tmp_b, ctx->chrom_cy,
                   ctx->chrom_cx, ctx->nuc_roots, ctx->counters, ctx->img_in, ctx->pre, ctx->dapi, ctx->labels,
                   ctx->d_n_ec, ctx->d_ec_px};
@@ -255,6 +258,133 @@ int ecseg_segment_image_host(ecseg_ctx* ctx, const void* h_img, int h, int w, in
   ECSEG_TRY(ecseg_segment_image_host_async(ctx, h_img, h, w, ch, bytes_per_sample, h_dapi, h_labels, flags, nullptr));
   return ecseg_segment_image_host_wait(ctx, n_ec, ec_px);
 }
+
+// ---- artefact file images (artifacts.cu) -----------------------------------------------------------------
+
+int ecseg_artifact_sizes(int h, int w, size_t* png_cap, size_t* npy_bytes, size_t* tif_bytes) {
+  if (h < 1 || w < 1) return ECSEG_E_INVALID;
+  if (png_cap) *png_cap = art_png_file_cap(h, w);
+  if (npy_bytes) *npy_bytes = art_npy_file_bytes(h, w);
+  if (tif_bytes) *tif_bytes = art_tiff_file_bytes(h, w);
+  return ECSEG_OK;
+}
+
+// enqueue the encoders of one image on `st`; results land in the host buffers / ctx->h_result after the stream drains
+static int enqueue_artifacts(ecseg_ctx* ctx, const uint8_t* d_labels, const uint8_t* d_dapi, int h, int w, uint8_t* h_tif,
+                             uint8_t* h_npy, uint8_t* h_png, size_t png_cap, cudaStream_t st) {
+  const size_t n_px = (size_t)h * w;
+  if (h_tif) {
+    if (!d_dapi) { ctx->err = "artefacts: no dapi plane"; return ECSEG_E_INVALID; }
+    hostfmt::tiff_header(h_tif, h, w);
+    ECSEG_CUDA(cudaMemcpyAsync(h_tif + hostfmt::kTiffDataOffset, d_dapi, n_px, cudaMemcpyDeviceToHost, st));
+  }
+  if (h_npy) {
+    ECSEG_TRY(art_ensure_workspace(ctx));
+    const size_t hdr = hostfmt::npy_header(h_npy, 4096, h, w);
+    ECSEG_TRY(art_widen_i64(ctx, d_labels, n_px, ctx->npy_i64, st));
+    ECSEG_CUDA(cudaMemcpyAsync(h_npy + hdr, ctx->npy_i64, n_px * 8, cudaMemcpyDeviceToHost, st));
+  }
+  ctx->job.h_png = h_png; ctx->job.png_cap = png_cap; ctx->job.h = h; ctx->job.w = w; ctx->job.st = st;
+  if (h_png) {
+    if (png_cap < hostfmt::png_file_bytes(8)) { ctx->err = "artefacts: png buffer too small"; return ECSEG_E_INVALID; }
+    ECSEG_TRY(art_png_encode(ctx, d_labels, h, w, st));
+    ECSEG_CUDA(cudaMemcpyAsync(&ctx->h_result->png_zlib_bytes, ctx->png_res, 8, cudaMemcpyDeviceToHost, st));
+    ECSEG_CUDA(cudaMemcpyAsync(ctx->h_png_stage, ctx->png_out, std::min(kPngFirstChunk, ctx->png_zcap), cudaMemcpyDeviceToHost, st));
+  }
+  return ECSEG_OK;
+}
+
+// after the stream drained: move the zlib stream into the caller's buffer and frame it as a PNG file
+static int finish_png(ecseg_ctx* ctx, size_t* png_bytes) {
+  if (png_bytes) *png_bytes = 0;
+  if (!ctx->job.h_png) return ECSEG_OK;
+  const size_t zb = ctx->h_result->png_zlib_bytes;
+  if (hostfmt::png_file_bytes(zb) > ctx->job.png_cap) { ctx->err = "artefacts: png buffer too small for this image"; return ECSEG_E_INVALID; }
+  uint8_t* dst = ctx->job.h_png + hostfmt::kPngDataOffset;
+  memcpy(dst, ctx->h_png_stage, std::min(zb, kPngFirstChunk));
+  if (zb > kPngFirstChunk) {
+    ECSEG_CUDA(cudaMemcpyAsync(dst + kPngFirstChunk, ctx->png_out + kPngFirstChunk, zb - kPngFirstChunk, cudaMemcpyDeviceToHost, ctx->job.st));
+    ECSEG_CUDA(cudaStreamSynchronize(ctx->job.st));
+  }
+  const size_t n = hostfmt::png_wrap(ctx->job.h_png, zb, ctx->job.h, ctx->job.w);
+  if (png_bytes) *png_bytes = n;
+  return ECSEG_OK;
+}
+
+int ecseg_overlay_png(ecseg_ctx* ctx, const uint8_t* d_labels, int h, int w, uint8_t* h_png, size_t cap, size_t* n_bytes,
+                      void* stream) {
+  API_GUARD(ctx);
+  ECSEG_TRY(check_hw(ctx, h, w, "ecseg_overlay_png"));
+  if (!d_labels || !h_png) { ctx->err = "ecseg_overlay_png: null pointer"; return ECSEG_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  ECSEG_TRY(enqueue_artifacts(ctx, d_labels, nullptr, h, w, nullptr, nullptr, h_png, cap, st));
+  ECSEG_CUDA(cudaStreamSynchronize(st));
+  return finish_png(ctx, n_bytes);
+}
+
+int ecseg_labels_npy(ecseg_ctx* ctx, const uint8_t* d_labels, int h, int w, uint8_t* h_npy, size_t cap, size_t* n_bytes,
+                     void* stream) {
+  API_GUARD(ctx);
+  ECSEG_TRY(check_hw(ctx, h, w, "ecseg_labels_npy"));
+  if (!d_labels || !h_npy || cap < art_npy_file_bytes(h, w)) { ctx->err = "ecseg_labels_npy: null pointer or buffer too small"; return ECSEG_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  ECSEG_TRY(enqueue_artifacts(ctx, d_labels, nullptr, h, w, nullptr, h_npy, nullptr, 0, st));
+  ECSEG_CUDA(cudaStreamSynchronize(st));
+  if (n_bytes) *n_bytes = art_npy_file_bytes(h, w);
+  return ECSEG_OK;
+}
+
+int ecseg_gray_tiff(ecseg_ctx* ctx, const uint8_t* d_plane, int h, int w, uint8_t* h_tif, size_t cap, size_t* n_bytes,
+                    void* stream) {
+  API_GUARD(ctx);
+  ECSEG_TRY(check_hw(ctx, h, w, "ecseg_gray_tiff"));
+  if (!d_plane || !h_tif || cap < art_tiff_file_bytes(h, w)) { ctx->err = "ecseg_gray_tiff: null pointer or buffer too small"; return ECSEG_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  ECSEG_TRY(enqueue_artifacts(ctx, nullptr, d_plane, h, w, h_tif, nullptr, nullptr, 0, st));
+  ECSEG_CUDA(cudaStreamSynchronize(st));
+  if (n_bytes) *n_bytes = art_tiff_file_bytes(h, w);
+  return ECSEG_OK;
+}
+
+int ecseg_segment_image_files_async(ecseg_ctx* ctx, const void* h_img, int h, int w, int ch, int bytes_per_sample,
+                                    uint8_t* h_tif, uint8_t* h_npy, uint8_t* h_png, size_t png_cap, uint8_t* h_labels,
+                                    int flags, void* stream) {
+  API_GUARD(ctx);
+  ECSEG_TRY(check_hw(ctx, h, w, "ecseg_segment_image_files"));
+  if (!h_img || (ch != 1 && ch != 3 && ch != 4) || (bytes_per_sample != 1 && bytes_per_sample != 2)) {
+    ctx->err = "ecseg_segment_image_files: bad arguments";
+    return ECSEG_E_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n_px = (size_t)h * w;
+  ECSEG_CUDA(cudaMemcpyAsync(ctx->img_in, h_img, n_px * ch * bytes_per_sample, cudaMemcpyHostToDevice, st));
+  ECSEG_TRY(ecseg_segment_image(ctx, ctx->img_in, h, w, ch, bytes_per_sample, h_tif ? ctx->dapi : nullptr, ctx->labels,
+                                ctx->d_n_ec, ctx->d_ec_px, flags, st));
+  ECSEG_TRY(enqueue_artifacts(ctx, ctx->labels, ctx->dapi, h, w, h_tif, h_npy, h_png, png_cap, st));
+  if (h_labels) ECSEG_CUDA(cudaMemcpyAsync(h_labels, ctx->labels, n_px, cudaMemcpyDeviceToHost, st));
+  ECSEG_CUDA(cudaMemcpyAsync(&ctx->h_result->n_ec, ctx->d_n_ec, 4, cudaMemcpyDeviceToHost, st));
+  ECSEG_CUDA(cudaMemcpyAsync(&ctx->h_result->ec_px, ctx->d_ec_px, 8, cudaMemcpyDeviceToHost, st));
+  ECSEG_CUDA(cudaMemcpyAsync(&ctx->h_result->device_error, &ctx->counters->device_error, 4, cudaMemcpyDeviceToHost, st));
+  ECSEG_CUDA(cudaEventRecord(ctx->ev_done, st));
+  ctx->pending = true;
+  return ECSEG_OK;
+}
+
+int ecseg_segment_image_files_wait(ecseg_ctx* ctx, int32_t* n_ec, int64_t* ec_px, size_t* png_bytes) {
+  ECSEG_TRY(ecseg_segment_image_host_wait(ctx, n_ec, ec_px));
+  return finish_png(ctx, png_bytes);
+}
+
+int ecseg_tiff_read(const char* path, void* h_dst, size_t cap, int* h, int* w, int* ch, int* bytes_per_sample) {
+  if (!path || !h || !w || !ch || !bytes_per_sample) return ECSEG_E_INVALID;
+  return art_tiff_read(path, h_dst, cap, h, w, ch, bytes_per_sample);
+}
+
+/* host-only format helpers, exposed so the no-GPU tests can pin them */
+size_t ecseg_png_wrap(uint8_t* file, size_t zlib_bytes, int h, int w) { return hostfmt::png_wrap(file, zlib_bytes, h, w); }
+size_t ecseg_npy_header(uint8_t* buf, size_t cap, int h, int w) { return hostfmt::npy_header(buf, cap, h, w); }
+size_t ecseg_tiff_header(uint8_t* buf, int h, int w) { return hostfmt::tiff_header(buf, h, w); }
+uint32_t ecseg_crc32(uint32_t crc, const uint8_t* p, size_t n) { return hostfmt::crc32_update(crc, p, n); }
 
 int ecseg_debug_layer_output(ecseg_ctx* ctx, int layer, int n, float* d_out, void* stream) {
   API_GUARD(ctx);

@@ -19,6 +19,7 @@ constexpr int kEcSizeThreshold = 15;  // EC_SIZE_THRESHOLD  (src/image_tools.py:
 constexpr int kMinChromCount = 5;     // src/image_tools.py:72
 constexpr double kChromWindow = 70.0; // src/image_tools.py:72
 constexpr int kHsrSizeThreshold = 20; // HSR_SIZE_THRESHOLD  (src/meta_overlay.py:12)
+constexpr size_t kPngFirstChunk = 1u << 20;  // bytes of the overlay's zlib stream copied to the host speculatively
 
 // Small device-resident scalar block, zeroed per stage by k_zero_counters.
 struct Counters {
@@ -88,10 +89,23 @@ struct ecseg_ctx {
   int64_t* d_ec_px = nullptr;
 
   // pinned result slot + completion event of the asynchronous host entry
-  struct HostResult { int32_t n_ec; int32_t device_error; int64_t ec_px; };
+  struct HostResult { int32_t n_ec; int32_t device_error; int64_t ec_px; uint32_t png_zlib_bytes; uint32_t png_adler; };
   HostResult* h_result = nullptr;
   cudaEvent_t ev_done = nullptr;
   bool pending = false;
+
+  // artefact encoders (artifacts.cu; allocated on first use)
+  uint8_t* png_slots = nullptr;          // one worst-case slot per scanline
+  uint8_t* png_out = nullptr;            // contiguous zlib stream
+  uint32_t* png_sizes = nullptr;         // fragment bytes per scanline
+  uint32_t* png_offs = nullptr;          // fragment offsets in png_out
+  unsigned long long* png_rs = nullptr;  // per-row Adler byte sum
+  unsigned long long* png_rt = nullptr;  // per-row Adler weighted sum
+  uint32_t* png_res = nullptr;           // {zlib bytes, adler}
+  int64_t* npy_i64 = nullptr;            // widened label map
+  uint8_t* h_png_stage = nullptr;        // pinned, kPngFirstChunk bytes
+  size_t png_zcap = 0;
+  struct FilesJob { uint8_t* h_png = nullptr; size_t png_cap = 0; int h = 0, w = 0; cudaStream_t st = nullptr; } job;
 
   ecseg::UNet* net = nullptr;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -148,6 +162,17 @@ int pp_count_colocalization(ecseg_ctx* ctx, const uint8_t* d_ob1, const uint8_t*
                             cudaStream_t st);
 int pp_remove_small_objects(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w, int min_size, uint8_t* d_out,
                             cudaStream_t st);
+
+// artifacts.cu
+size_t art_png_zlib_cap(int h, int w);
+size_t art_png_file_cap(int h, int w);
+size_t art_npy_file_bytes(int h, int w);
+size_t art_tiff_file_bytes(int h, int w);
+int art_ensure_workspace(ecseg_ctx* ctx);
+void art_free_workspace(ecseg_ctx* ctx);
+int art_png_encode(ecseg_ctx* ctx, const uint8_t* d_labels, int h, int w, cudaStream_t st);
+int art_widen_i64(ecseg_ctx* ctx, const uint8_t* d_labels, size_t n, int64_t* d_out, cudaStream_t st);
+int art_tiff_read(const char* path, void* dst, size_t cap, int* h, int* w, int* ch, int* bps);
 
 int unet_create(ecseg_ctx* ctx);
 void unet_destroy(ecseg_ctx* ctx);

@@ -266,6 +266,55 @@ class Engine:
         self._chk(self.lib.ecseg_segment_image_host_wait(self.ctx, byref(n), byref(px)))
         return n.value, px.value
 
+    # -- artefact file images -------------------------------------------------------------------
+    @staticmethod
+    def artifact_sizes(h: int, w: int):
+        """(png worst-case capacity, npy file bytes, tif file bytes) for an h x w image."""
+        a, b, c = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+        if _lib.load().ecseg_artifact_sizes(h, w, byref(a), byref(b), byref(c)) != 0:
+            raise ValueError("bad image shape")
+        return a.value, b.value, c.value
+
+    def _file_image(self, fn, plane, cap: int) -> np.ndarray:
+        d = self._dev(plane, torch.uint8)
+        h, w = d.shape
+        buf = np.empty(cap, np.uint8)
+        n = ctypes.c_size_t()
+        self._chk(fn(self.ctx, d.data_ptr(), h, w, buf.ctypes.data_as(c_void_p), cap, byref(n), self._stream()))
+        return buf[:n.value]
+
+    def overlay_png(self, labels) -> np.ndarray:
+        """labels/<stem>.png of the reference (src/metaseg.py:47-52) as PNG file bytes, encoded on the GPU."""
+        h, w = labels.shape
+        return self._file_image(self.lib.ecseg_overlay_png, labels, self.artifact_sizes(h, w)[0])
+
+    def labels_npy(self, labels) -> np.ndarray:
+        """labels/<stem>.npy of the reference (np.save of the int64 map, src/metaseg.py:53) as file bytes."""
+        h, w = labels.shape
+        return self._file_image(self.lib.ecseg_labels_npy, labels, self.artifact_sizes(h, w)[1])
+
+    def gray_tiff(self, plane) -> np.ndarray:
+        """dapi/<name> of the reference (cv2.imwrite of an 8-bit plane, src/utils.py:122-123) as TIFF file bytes."""
+        h, w = plane.shape
+        return self._file_image(self.lib.ecseg_gray_tiff, plane, self.artifact_sizes(h, w)[2])
+
+    def segment_files_async(self, img: np.ndarray, tif: np.ndarray | None, npy: np.ndarray | None, png: np.ndarray | None,
+                            labels_out: np.ndarray | None = None, faithful_merge=False, stream=None):
+        """Enqueue one image: H2D, the whole path, the three file images, D2H.  Buffers are uint8 arrays sized by
+        artifact_sizes (tif / npy pinned); pair with segment_files_wait()."""
+        h, w = img.shape[:2]
+        ch = 1 if img.ndim == 2 else img.shape[2]
+        p = lambda a: a.ctypes.data_as(c_void_p) if a is not None else None
+        self._chk(self.lib.ecseg_segment_image_files_async(
+            self.ctx, p(img), h, w, ch, img.dtype.itemsize, p(tif), p(npy), p(png), png.size if png is not None else 0,
+            p(labels_out), PP_FAITHFUL_MERGE if faithful_merge else 0, stream if stream is not None else self._stream()))
+
+    def segment_files_wait(self):
+        """-> (n_ec, ec_px, png file bytes) of the image enqueued by segment_files_async."""
+        n, px, nb = c_int32(), c_int64(), ctypes.c_size_t()
+        self._chk(self.lib.ecseg_segment_image_files_wait(self.ctx, byref(n), byref(px), byref(nb)))
+        return n.value, px.value, nb.value
+
     def last_stage_ms(self):
         ms = (c_float * 4)()
         self._chk(self.lib.ecseg_last_stage_ms(self.ctx, ms))

@@ -28,6 +28,13 @@ def save_overlay(path_png: str, I: np.ndarray) -> None:
     cv2.imwrite(path_png, _PALETTE_BGRA[np.clip(I, 0, 3)])
 
 
+def _shape_of(path):
+    """(h, w, ch, bytes per sample) through the general decoder, for TIFF flavours the fast reader does not probe."""
+    from .utils import imread
+    a = imread(path)
+    return a.shape[0], a.shape[1], (1 if a.ndim == 2 else a.shape[2]), a.dtype.itemsize
+
+
 def main(argv):
     config = open("config.yaml")
     var = yaml.load(config, Loader=yaml.FullLoader)['metaseg']
@@ -48,6 +55,25 @@ def main(argv):
     rows = []
     print("Reading from: ", inpath)
     path_split = None
+    # *.tif inputs: decode, GPU path and the three writes overlap (ecseg_b200/pipeline.py); the GPU hands back
+    # complete file images (PNG deflated on the device, int64 .npy payload, TIFF), the host only write()s them.
+    tifs = [p for p in image_paths if p.lower().endswith('.tif')]
+    if tifs and not os.environ.get("ECSEG_SERIAL"):
+        from . import tiffio
+        from .pipeline import FilesPipeline
+        shapes = [tiffio.probe(p) or _shape_of(p) for p in tifs]
+        opt = var if isinstance(var, dict) else {}
+        pipe = FilesPipeline(model.weights, model.precision, max(max(s[0] for s in shapes), 256),
+                             max(max(s[1] for s in shapes), 256), n_ctx=int(opt.get('contexts', 2)),
+                             n_readers=int(opt.get('readers', 4)), n_writers=int(opt.get('writers', 6)),
+                             max_bytes_per_px=max(s[2] * s[3] for s in shapes), verbose=True)
+        try:
+            for p, n_ec in pipe.run(tifs):
+                path_split = os.path.split(p)
+                rows.append((path_split[1], n_ec))
+        finally:
+            pipe.close()
+        image_paths = [p for p in image_paths if p not in set(tifs)]
     for i in image_paths:
         print("Processing image: ", i)
         I = meta_segment(model, i)

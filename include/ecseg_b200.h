@@ -155,6 +155,48 @@ int ecseg_segment_image_host_async(ecseg_ctx* ctx, const void* h_img, int h, int
                                    uint8_t* h_dapi, uint8_t* h_labels, int flags, void* stream);
 int ecseg_segment_image_host_wait(ecseg_ctx* ctx, int32_t* n_ec, int64_t* ec_px);
 
+/* ---- artefact file images and input decode ("next" rows f-2/f-3) ---------- */
+
+/* The three files src/metaseg.py writes per image are produced as complete FILE IMAGES in host memory, so the host
+ * only write()s them:
+ *   labels/<stem>.png  (plt.imsave with the 4-colour ListedColormap, src/metaseg.py:47-52): RGBA8 PNG whose scanlines
+ *                      are palette-expanded, PNG-filtered and deflated ON THE GPU (one thread block per scanline,
+ *                      fixed-Huffman blocks closed by sync flushes); RGBA never exists in memory.
+ *   labels/<stem>.npy  (np.save of the int64 map, src/metaseg.py:53): .npy v1.0 header + payload widened on the GPU.
+ *   dapi/<name>        (cv2.imwrite(255 - I), src/utils.py:112,122-123): baseline 8-bit gray TIFF, one strip.
+ * ecseg_artifact_sizes gives the buffer sizes: png_cap is the worst case (every byte a 9-bit literal, about 1.13x the
+ * raw RGBA size; a label map typically needs ~1 % of it), npy_bytes / tif_bytes are exact. */
+int ecseg_artifact_sizes(int h, int w, size_t* png_cap, size_t* npy_bytes, size_t* tif_bytes);
+
+/* Stand-alone encoders: device plane in, host file image out, synchronous on `stream`. *n_bytes = file length. */
+int ecseg_overlay_png(ecseg_ctx* ctx, const uint8_t* d_labels, int h, int w, uint8_t* h_png, size_t cap, size_t* n_bytes,
+                      void* stream);
+int ecseg_labels_npy(ecseg_ctx* ctx, const uint8_t* d_labels, int h, int w, uint8_t* h_npy, size_t cap, size_t* n_bytes,
+                     void* stream);
+int ecseg_gray_tiff(ecseg_ctx* ctx, const uint8_t* d_plane, int h, int w, uint8_t* h_tif, size_t cap, size_t* n_bytes,
+                    void* stream);
+
+/* ecseg_segment_image_host_async / _wait plus the file images: the per-image body of src/metaseg.py:42-53 minus the
+ * write() calls.  h_tif / h_npy / h_png / h_labels are nullable; h_tif and h_npy should be pinned, h_png may be
+ * pageable (it is filled by _wait from a pinned staging buffer).  *png_bytes = length of the PNG file image. */
+int ecseg_segment_image_files_async(ecseg_ctx* ctx, const void* h_img, int h, int w, int ch, int bytes_per_sample,
+                                    uint8_t* h_tif, uint8_t* h_npy, uint8_t* h_png, size_t png_cap, uint8_t* h_labels,
+                                    int flags, void* stream);
+int ecseg_segment_image_files_wait(ecseg_ctx* ctx, int32_t* n_ec, int64_t* ec_px, size_t* png_bytes);
+
+/* Replaces skimage.io.imread for the common microscope layout (src/utils.py:110): little-endian classic TIFF, single
+ * page, uncompressed strips, chunky, unsigned 8/16-bit, 1/3/4 samples.  Samples are read (pread) straight into h_dst
+ * (e.g. pinned memory) in stored order.  h_dst == NULL only probes the shape.  Returns 0 on success; > 0 when the
+ * file is some other TIFF flavour (the caller uses a general decoder); -1 cannot open; -2 h_dst too small.  Host only. */
+int ecseg_tiff_read(const char* path, void* h_dst, size_t cap, int* h, int* w, int* ch, int* bytes_per_sample);
+
+/* Host-side format helpers behind the calls above (no GPU needed): PNG framing of a zlib stream that sits at byte 41
+ * of `file`, the .npy header for int64 [h,w], the 128-byte TIFF header, CRC-32. */
+size_t ecseg_png_wrap(uint8_t* file, size_t zlib_bytes, int h, int w);
+size_t ecseg_npy_header(uint8_t* buf, size_t cap, int h, int w);
+size_t ecseg_tiff_header(uint8_t* buf, int h, int w);
+uint32_t ecseg_crc32(uint32_t crc, const uint8_t* p, size_t n);
+
 /* ---- introspection used by tests and bench.py ----------------------------------------------- */
 
 /* Copy the activation a U-Net layer produced in the last forward as float32 NHWC
