@@ -52,6 +52,11 @@ int ecseg_ctx_create(ecseg_ctx** out, int device, int max_h, int max_w, int max_
   A((void**)&ctx->flag, P * 4); A((void**)&ctx->tmp_a, P); A((void**)&ctx->tmp_b, P);
   A((void**)&ctx->chrom_cy, (P / 4 + 16) * 8); A((void**)&ctx->chrom_cx, (P / 4 + 16) * 8);
   A((void**)&ctx->nuc_roots, (P / 4 + 16) * 4);
+  {  // 32x32 tiles of the largest image, 1024 root slots each (worst aspect ratio: every row / column a partial tile)
+    ctx->max_ccl_tiles = ((size_t)max_h / 32 + 1) * ((size_t)max_w / 32 + 1) + ((size_t)max_h + (size_t)max_w) / 16 + 64;
+    A((void**)&ctx->root_list, ctx->max_ccl_tiles * 1024 * 4);
+    A((void**)&ctx->tile_nroots, ctx->max_ccl_tiles * 4);
+  }
   A((void**)&ctx->counters, sizeof(Counters));
   A((void**)&ctx->img_in, P * 8); A((void**)&ctx->pre, P); A((void**)&ctx->dapi, P); A((void**)&ctx->labels, P);
   A((void**)&ctx->d_n_ec, 8); A((void**)&ctx->d_ec_px, 8);
@@ -72,7 +77,7 @@ void ecseg_ctx_destroy(ecseg_ctx* ctx) {
   unet_destroy(ctx);
   art_free_workspace(ctx);
   void* ptrs[] = {ctx->L, ctx->area, ctx->sum_y, ctx->sum_x, ctx->flag, ctx->tmp_a, ctx->tmp_b, ctx->chrom_cy,
-                  ctx->chrom_cx, ctx->nuc_roots, ctx->counters, ctx->img_in, ctx->pre, ctx->dapi, ctx->labels,
+                  ctx->chrom_cx, ctx->nuc_roots, ctx->root_list, ctx->tile_nroots, ctx->counters, ctx->img_in, ctx->pre, ctx->dapi, ctx->labels,
                   ctx->d_n_ec, ctx->d_ec_px};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);

@@ -35,6 +35,9 @@ struct Counters {
   int range_error;                 // img_as_ubyte range violation seen
   int device_error;                // tcgen05 pipeline watchdog
   int ov_hits[4];                  // meta_overlay: components flagged per colocalisation test
+  // per labelling run, double buffered by run parity (a run clears the other parity's slots for the next run)
+  unsigned long long npix_run[2];  // foreground pixels
+  unsigned long long npix_cls[2][4];  // pixels per class value
 };
 
 struct TileGrid {
@@ -78,6 +81,10 @@ struct ecseg_ctx {
   double* chrom_cy = nullptr;           // compacted chromosome centroids
   double* chrom_cx = nullptr;
   int32_t* nuc_roots = nullptr;         // compacted nucleus roots
+  int32_t* root_list = nullptr;         // tile-local component roots of the current labelling, 1024 slots per 32x32 tile
+  int32_t* tile_nroots = nullptr;       // entries used per tile
+  size_t max_ccl_tiles = 0;             // tiles the two arrays above are sized for
+  int ccl_parity = 0;
   ecseg::Counters* counters = nullptr;
 
   // whole-image path workspace

@@ -81,12 +81,17 @@ static inline dim3 px_block() { return dim3(32, 8); }
 // Connected-component labelling in three passes:
 //   k_ccl_tile    one block per 32x32 tile: horizontal runs by warp ballot, vertical / diagonal unions
 //                 with atomicMin on SHARED-memory labels, then every pixel is written once to global
-//                 memory pointing at its tile-local root (global linear index).  Tile roots reset their
-//                 statistics slots.  Global memory sees 1 B read + 4 B written per pixel and no atomics.
+//                 memory pointing at its tile-local root (global linear index).  Per tile-local component
+//                 the block also reduces area / coordinate sums / image-border contact in shared memory,
+//                 stores them at the tile root's slot and appends the tile root to a compact ROOT LIST;
+//                 class histograms are reduced per block.  Global memory sees 1 B read + 4 B written per
+//                 pixel and a handful of atomics per block.
 //   k_ccl_border  only the pixels on tile borders (1/16 of the image) union across tiles with global
-//                 atomicMin.
-//   k_ccl_finish  every pixel resolves its final root (tile root -> short chain), optional per-component
-//                 area / coordinate sums (warp-aggregated), root and pixel counts.
+//                 atomicMin (root entries only ever change in this pass).
+//   k_ccl_roots   walks the ROOT LIST (not the image): flattens every tile root onto its global root, folds
+//                 its statistics into the global root's slot, counts components.  Afterwards every
+//                 pixel reaches its component in exactly two hops, root_of() = L[L[i]], which is what the
+//                 consumer kernels use -- there is no per-pixel relabelling pass.
 // ------------------------------------------------------------------------------------------------
 constexpr int kCclTile = 32;
 
@@ -106,32 +111,130 @@ __device__ __forceinline__ void ufs_union(int* sl, int a, int b) {
   }
 }
 
-__global__ void __launch_bounds__(256) k_ccl_tile(const uint8_t* __restrict__ cls, int h, int w, int mode, int c, int conn8,
-                                                  int32_t* __restrict__ L, int32_t* __restrict__ area,
+// component of pixel i after k_ccl_roots: pixel -> tile root -> global root; -1 for background
+__device__ __forceinline__ int root_of(const int32_t* __restrict__ L, int i) {
+  const int a = L[i];
+  return a < 0 ? -1 : L[a];
+}
+
+enum { FIN_AREA = 1, FIN_CENTROID = 2, FIN_CLASS_PIX = 4, FIN_LAST_ROOT = 8, FIN_TOUCH = 16 };
+
+// Point-wise rule kernels run on the flat pixel array, 8 pixels per thread: one 8-byte class load, two 16-byte
+// label loads, per-pixel gathers of the component slot only where the rule can fire.
+constexpr int kPxPerThread = 8;
+static inline int flat_blocks(long long n_px) { return cdiv(cdiv(n_px, kPxPerThread), 256); }
+
+struct Px8 {
+  uint8_t v[8];
+  int a[8];
+};
+__device__ __forceinline__ bool load_px8(const uint8_t* __restrict__ cls, const int32_t* __restrict__ L, long long n_px,
+                                         long long i0, Px8& p, int& n) {
+  if (i0 >= n_px) return false;
+  n = (int)min((long long)kPxPerThread, n_px - i0);
+  if (n == kPxPerThread) {
+    const uint2 c = *reinterpret_cast<const uint2*>(cls + i0);
+    const int4 l0 = *reinterpret_cast<const int4*>(L + i0), l1 = *reinterpret_cast<const int4*>(L + i0 + 4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { p.v[k] = (uint8_t)(c.x >> (8 * k)); p.v[4 + k] = (uint8_t)(c.y >> (8 * k)); }
+    p.a[0] = l0.x; p.a[1] = l0.y; p.a[2] = l0.z; p.a[3] = l0.w; p.a[4] = l1.x; p.a[5] = l1.y; p.a[6] = l1.z; p.a[7] = l1.w;
+  } else {
+    for (int k = 0; k < n; ++k) { p.v[k] = cls[i0 + k]; p.a[k] = L[i0 + k]; }
+  }
+  return true;
+}
+__device__ __forceinline__ void store_px8(uint8_t* __restrict__ cls, long long i0, const Px8& p, int n) {
+  if (n == kPxPerThread) {
+    uint2 c;
+    c.x = p.v[0] | (p.v[1] << 8) | (p.v[2] << 16) | ((unsigned)p.v[3] << 24);
+    c.y = p.v[4] | (p.v[5] << 8) | (p.v[6] << 16) | ((unsigned)p.v[7] << 24);
+    *reinterpret_cast<uint2*>(cls + i0) = c;
+  } else {
+    for (int k = 0; k < n; ++k) cls[i0 + k] = p.v[k];
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_ccl_tile(const uint8_t* __restrict__ cls, int h, int w, int c, int conn8,
+                                                  int what, int par, int32_t* __restrict__ L, int32_t* __restrict__ area,
                                                   unsigned long long* __restrict__ sy, unsigned long long* __restrict__ sx,
-                                                  int32_t* __restrict__ flag, Counters* __restrict__ cnt) {
+                                                  int32_t* __restrict__ flag, int32_t* __restrict__ roots,
+                                                  int32_t* __restrict__ tile_nroots, Counters* __restrict__ cnt) {
   __shared__ uint8_t sk[kCclTile][kCclTile + 4];
   __shared__ int sl[kCclTile * kCclTile];
+  __shared__ int s_area[kCclTile * kCclTile];
+  __shared__ unsigned s_sy[kCclTile * kCclTile], s_sx[kCclTile * kCclTile];
+  __shared__ uint8_t s_touch[kCclTile * kCclTile];
+  __shared__ unsigned s_hist[4], s_fg, s_nroots;
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const int x0 = blockIdx.x * kCclTile, y0 = blockIdx.y * kCclTile;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4) {     // per-run counters (k_ccl_finish runs later)
-    cnt->ncomp[threadIdx.x] = 0; cnt->npix[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { cnt->n_chrom = 0; cnt->n_nuc = 0; cnt->last_root = -1; }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4) {     // per-run counters (k_ccl_roots runs later)
+    cnt->ncomp[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { cnt->n_chrom = 0; cnt->n_nuc = 0; cnt->last_root = -1; cnt->npix_run[par ^ 1] = 0; }
     cnt->ov_hits[threadIdx.x] = 0;
+    cnt->npix_cls[par ^ 1][threadIdx.x] = 0;
   }
+  if (threadIdx.x < 4) s_hist[threadIdx.x] = 0;
+  if (threadIdx.x == 0) { s_fg = 0; s_nroots = 0; }
   const int x = x0 + lane;
+  const bool want_c = (what & FIN_CENTROID) != 0;
+  const bool want_a = (what & (FIN_AREA | FIN_CENTROID)) != 0;
+  const bool all_in = x0 + kCclTile <= w && y0 + kCclTile <= h;
+  const bool edge_tile = (what & FIN_TOUCH) && (x0 == 0 || y0 == 0 || x0 + kCclTile >= w || y0 + kCclTile >= h);
+  int kk[4];
 #pragma unroll
   for (int ps = 0; ps < 4; ++ps) {
     const int row = wp + 8 * ps, y = y0 + row;
-    const int k = (y < h && x < w) ? key_of(cls[(size_t)y * w + x], mode, c) : 0;
+    const int v = (y < h && x < w) ? cls[y * w + x] : 0;
+    const int k = (y < h && x < w) ? key_of((uint8_t)v, MODE, c) : 0;
+    kk[ps] = k;
     sk[row][lane] = (uint8_t)k;
     const int kl = __shfl_up_sync(0xffffffffu, k, 1);
     const bool same = lane > 0 && kl == k;
     const unsigned heads = ~__ballot_sync(0xffffffffu, same);
     const int head = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-    sl[row * 32 + lane] = row * 32 + head;      // background pixels form runs too; they are never unioned vertically
+    const int i = row * 32 + lane;
+    sl[i] = row * 32 + head;      // background pixels form runs too; they are never unioned vertically
+    if (want_a) s_area[i] = 0;
+    if (edge_tile) s_touch[i] = 0;
+    if (want_c) { s_sy[i] = 0; s_sx[i] = 0; }
+    if (what & FIN_CLASS_PIX) {     // pixels per class value (size_thresh's sum of areas per class)
+#pragma unroll
+      for (int q = 1; q < 4; ++q) {
+        const unsigned b = __ballot_sync(0xffffffffu, v == q);
+        if (lane == 0 && b) atomicAdd(&s_hist[q], (unsigned)__popc(b));
+      }
+    }
   }
   __syncthreads();
+  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+  int32_t* my_roots = roots + (size_t)tile * (kCclTile * kCclTile);
+  // Uniform tiles (all background, or one key over a full tile) are the common case on real label maps -- most of
+  // an image is background for the class labellings and foreground for the complement labellings of fill_holes --
+  // and need no union-find at all.
+  const int kref = sk[0][0];
+  if (__syncthreads_and(kk[0] == kref && kk[1] == kref && kk[2] == kref && kk[3] == kref) && (kref == 0 || all_in)) {
+    const int g0 = y0 * w + x0;
+#pragma unroll
+    for (int ps = 0; ps < 4; ++ps) {
+      const int y = y0 + wp + 8 * ps;
+      if (y < h && x < w) L[y * w + x] = kref ? g0 : -1;
+    }
+    if (threadIdx.x == 0) {
+      tile_nroots[tile] = kref ? 1 : 0;
+      if (kref) {
+        constexpr int n = kCclTile * kCclTile, tri = kCclTile * (kCclTile * (kCclTile - 1) / 2);
+        area[g0] = n;
+        if (want_c) { sy[g0] = (unsigned long long)n * (unsigned)y0 + tri; sx[g0] = (unsigned long long)n * (unsigned)x0 + tri; }
+        flag[g0] = edge_tile ? 1 : 0;
+        my_roots[0] = g0;
+        atomicAdd(&cnt->npix_run[par], (unsigned long long)n);
+      }
+    }
+    if ((what & FIN_CLASS_PIX) && threadIdx.x >= 1 && threadIdx.x < 4 && s_hist[threadIdx.x])
+      atomicAdd(&cnt->npix_cls[par][threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
+    return;
+  }
 #pragma unroll
   for (int ps = 0; ps < 4; ++ps) {
     const int row = wp + 8 * ps;
@@ -150,25 +253,87 @@ __global__ void __launch_bounds__(256) k_ccl_tile(const uint8_t* __restrict__ cl
     }
   }
   __syncthreads();
+  int rr[4];
 #pragma unroll
   for (int ps = 0; ps < 4; ++ps) {
     const int row = wp + 8 * ps, y = y0 + row;
-    if (y < h && x < w) {
-      const int i = row * 32 + lane;
+    const int i = row * 32 + lane;
+    const bool inb = y < h && x < w;
+    const bool fg = inb && sk[row][lane];
+    rr[ps] = -1;
+    if (inb) {
       const size_t gi = (size_t)y * w + x;
-      if (sk[row][lane]) {
+      if (fg) {
         const int r = ufs_find(sl, i);
+        rr[ps] = r;
         L[gi] = (y0 + (r >> 5)) * w + x0 + (r & 31);
-        if (r == i) { area[gi] = 0; sy[gi] = 0ull; sx[gi] = 0ull; flag[gi] = 0; }
       } else {
         L[gi] = -1;
       }
     }
+    const unsigned act = __ballot_sync(0xffffffffu, fg);
+    if (lane == 0 && act) atomicAdd(&s_fg, (unsigned)__popc(act));
+    if (fg && want_a) {
+      const int r = rr[ps];
+      const unsigned peers = __match_any_sync(act, r);
+      if (lane == __ffs(peers) - 1) {
+        const int n = __popc(peers);
+        atomicAdd(&s_area[r], n);
+        if (want_c) {
+          unsigned m = peers, sxs = 0;
+          while (m) { sxs += (unsigned)(__ffs(m) - 1); m &= m - 1; }
+          atomicAdd(&s_sy[r], (unsigned)(n * row));
+          atomicAdd(&s_sx[r], sxs);
+        }
+      }
+    }
+    if (fg && edge_tile && (y == 0 || y == h - 1 || x == 0 || x == w - 1)) s_touch[rr[ps]] = 1;
+  }
+  __syncthreads();
+  // tile roots: statistics slot + entry in the root list
+  unsigned rb[4];
+  int n_mine = 0;
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    const int i = (wp + 8 * ps) * 32 + lane;
+    rb[ps] = __ballot_sync(0xffffffffu, rr[ps] == i);
+    n_mine += __popc(rb[ps]);
+  }
+  int woff = 0;
+  if (lane == 0 && n_mine) woff = (int)atomicAdd(&s_nroots, (unsigned)n_mine);
+  woff = __shfl_sync(0xffffffffu, woff, 0);
+  __syncthreads();
+  // the tile's slice of the root list: entries [tile * 1024, tile * 1024 + n), n in tile_nroots[tile]
+  if (threadIdx.x == 0) {
+    tile_nroots[tile] = (int)s_nroots;
+    if (s_fg) atomicAdd(&cnt->npix_run[par], (unsigned long long)s_fg);
+  }
+  if ((what & FIN_CLASS_PIX) && threadIdx.x >= 1 && threadIdx.x < 4 && s_hist[threadIdx.x])
+    atomicAdd(&cnt->npix_cls[par][threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
+  int before = 0;
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    const int row = wp + 8 * ps;
+    const int i = row * 32 + lane;
+    if (rr[ps] == i) {
+      const int gi = (y0 + row) * w + x;
+      const int n = want_a ? s_area[i] : 0;
+      area[gi] = n;
+      if (want_c) {
+        sy[gi] = (unsigned long long)n * (unsigned)y0 + s_sy[i];
+        sx[gi] = (unsigned long long)n * (unsigned)x0 + s_sx[i];
+      }
+      flag[gi] = edge_tile ? s_touch[i] : 0;
+      my_roots[woff + before + __popc(rb[ps] & ((1u << lane) - 1u))] = gi;
+    }
+    before += __popc(rb[ps]);
   }
 }
 
 // Unions across tile borders.  Thread t < n_hb*w handles a pixel of a tile's top row (neighbours in the row
-// above), the rest a pixel of a tile's left column (neighbours in the column to the left).
+// above), the rest a pixel of a tile's left column (neighbours in the column to the left).  A pixel whose
+// predecessor along the border links the same two runs (same key here, before, and in both neighbours across the
+// border) skips its union: one union per pair of touching runs instead of one per pixel.
 __global__ void k_ccl_border(const uint8_t* __restrict__ cls, int h, int w, int mode, int c, int conn8,
                              int32_t* __restrict__ L) {
   const int n_hb = (h - 1) / kCclTile, n_vb = (w - 1) / kCclTile;
@@ -179,7 +344,12 @@ __global__ void k_ccl_border(const uint8_t* __restrict__ cls, int h, int w, int 
     const int i = y * w + x;
     const int k = key_of(cls[i], mode, c);
     if (!k) return;
-    if (key_of(cls[i - w], mode, c) == k) { uf_union(L, i, i - w); return; }
+    if (key_of(cls[i - w], mode, c) == k) {
+      // the pixel to the left belongs to the same tile unless x is a tile's first column
+      const bool dup = (x % kCclTile) != 0 && key_of(cls[i - 1], mode, c) == k && key_of(cls[i - w - 1], mode, c) == k;
+      if (!dup) uf_union(L, i, i - w);
+      return;
+    }
     if (!conn8) return;
     if (x > 0 && key_of(cls[i - w - 1], mode, c) == k) uf_union(L, i, i - w - 1);
     if (x < w - 1 && key_of(cls[i - w + 1], mode, c) == k) uf_union(L, i, i - w + 1);
@@ -190,98 +360,95 @@ __global__ void k_ccl_border(const uint8_t* __restrict__ cls, int h, int w, int 
     const int i = y * w + x;
     const int k = key_of(cls[i], mode, c);
     if (!k) return;
-    if (key_of(cls[i - 1], mode, c) == k) { uf_union(L, i, i - 1); return; }
+    if (key_of(cls[i - 1], mode, c) == k) {
+      const bool dup = (y % kCclTile) != 0 && key_of(cls[i - w], mode, c) == k && key_of(cls[i - w - 1], mode, c) == k;
+      if (!dup) uf_union(L, i, i - 1);
+      return;
+    }
     if (!conn8) return;
     if (y > 0 && key_of(cls[i - w - 1], mode, c) == k) uf_union(L, i, i - w - 1);
     if (y < h - 1 && key_of(cls[i + w - 1], mode, c) == k) uf_union(L, i, i + w - 1);
   }
 }
 
-enum { FIN_AREA = 1, FIN_CENTROID = 2, FIN_CLASS_PIX = 4, FIN_LAST_ROOT = 8 };
-
-// Final roots + reductions.  Roots are pixels with L[i] == i (root entries are stable once the unions are done).
-__global__ void __launch_bounds__(256) k_ccl_finish(const uint8_t* __restrict__ cls, int h, int w, int mode, int c, int what,
-                                                    int32_t* __restrict__ L, int32_t* __restrict__ area,
-                                                    unsigned long long* __restrict__ sy, unsigned long long* __restrict__ sx,
-                                                    Counters* __restrict__ cnt) {
-  __shared__ unsigned int s_fg, s_cls[4], s_roots[4];
+// Root-list pass, one warp per tile: flatten tile roots, fold statistics into the global roots, count components
+// per key class.
+__global__ void __launch_bounds__(256) k_ccl_roots(const uint8_t* __restrict__ cls, int n_tiles, int mode, int c, int what, int par,
+                                                   const int32_t* __restrict__ roots, const int32_t* __restrict__ tile_nroots,
+                                                   int32_t* __restrict__ L, int32_t* __restrict__ area,
+                                                   unsigned long long* __restrict__ sy, unsigned long long* __restrict__ sx,
+                                                   int32_t* __restrict__ flag, Counters* __restrict__ cnt) {
+  __shared__ unsigned s_roots[4];
   __shared__ int s_last;
-  const int tid = threadIdx.y * 32 + threadIdx.x;
-  if (tid < 4) { s_cls[tid] = 0; s_roots[tid] = 0; }
-  if (tid == 0) { s_fg = 0; s_last = -1; }
+  if (threadIdx.x < 4) s_roots[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_last = -1;
   __syncthreads();
-  const int x = blockIdx.x * 32 + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  int r = -1, v = 0, kroot = -1;
-  if (y < h && x < w) {
-    const int i = y * w + x;
-    const int l0 = L[i];
-    if (l0 >= 0) {
-      r = uf_find(L, l0);
-      if (r != l0) L[i] = r;
-      v = cls[i];
-      if (r == i) kroot = key_of((uint8_t)v, mode, c) & 3;
-    }
-  }
-  const bool valid = r >= 0;
-  const unsigned act = __ballot_sync(0xffffffffu, valid);
-  if (threadIdx.x == 0 && act) atomicAdd(&s_fg, (unsigned)__popc(act));
-  if (what & (FIN_AREA | FIN_CENTROID)) {
-    if (valid) {
-      const unsigned peers = __match_any_sync(act, r);
-      if ((int)threadIdx.x == __ffs(peers) - 1) {
-        const int n = __popc(peers);
-        atomicAdd(area + r, n);
-        if (what & FIN_CENTROID) {
-          unsigned m = peers;
-          unsigned long long sxs = 0;
-          while (m) { sxs += (unsigned)(__ffs(m) - 1); m &= m - 1; }
-          atomicAdd(sy + r, (unsigned long long)n * (unsigned)y);
-          atomicAdd(sx + r, sxs + (unsigned long long)n * (unsigned)(blockIdx.x * 32));
-        }
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  unsigned nk[4] = {0, 0, 0, 0};
+  int last = -1;
+  if (warp < n_tiles) {
+    const int n = tile_nroots[warp];
+    const int32_t* my = roots + (size_t)warp * (kCclTile * kCclTile);
+    for (int j = lane; j < n; j += 32) {
+      const int i = my[j];
+      const int R = uf_find(L, i);
+      if (R != i) {
+        L[i] = R;
+        if (what & (FIN_AREA | FIN_CENTROID)) atomicAdd(area + R, area[i]);
+        if (what & FIN_CENTROID) { atomicAdd(sy + R, sy[i]); atomicAdd(sx + R, sx[i]); }
+        if ((what & FIN_TOUCH) && flag[i]) flag[R] = 1;
+      } else {
+        nk[key_of(cls[i], mode, c) & 3]++;
+        last = max(last, i);
       }
     }
   }
-  // roots per key class (warp-aggregated), raster-last root
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const unsigned b = __ballot_sync(0xffffffffu, kroot == k);
-    if (threadIdx.x == 0 && b) atomicAdd(&s_roots[k], (unsigned)__popc(b));
+    unsigned v = nk[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && v) atomicAdd(&s_roots[k], v);
   }
   if (what & FIN_LAST_ROOT) {
-    int lr = kroot >= 0 ? y * w + x : -1;
-    for (int o = 16; o > 0; o >>= 1) lr = max(lr, __shfl_xor_sync(0xffffffffu, lr, o));
-    if (threadIdx.x == 0 && lr >= 0) atomicMax(&s_last, lr);
-  }
-  if (what & FIN_CLASS_PIX) {
-#pragma unroll
-    for (int k = 1; k < 4; ++k) {
-      const unsigned b = __ballot_sync(0xffffffffu, v == k);
-      if (threadIdx.x == 0 && b) atomicAdd(&s_cls[k], (unsigned)__popc(b));
-    }
+    for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+    if (lane == 0 && last >= 0) atomicMax(&s_last, last);
   }
   __syncthreads();
-  if (tid < 4) {
-    if (s_roots[tid]) atomicAdd(&cnt->ncomp[tid], (int)s_roots[tid]);
-    if (tid > 0 && s_cls[tid]) atomicAdd(&cnt->npix[tid], (unsigned long long)s_cls[tid]);
-  }
-  if (tid == 0) {
-    if (s_fg) atomicAdd(&cnt->npix[0], (unsigned long long)s_fg);
-    if (s_last >= 0) atomicMax(&cnt->last_root, s_last);
-  }
+  if (threadIdx.x < 4 && s_roots[threadIdx.x]) atomicAdd(&cnt->ncomp[threadIdx.x], (int)s_roots[threadIdx.x]);
+  if (threadIdx.x == 0 && s_last >= 0) atomicMax(&cnt->last_root, s_last);
+  // hand the per-run pixel counters over in the layout the rule kernels read
+  if (blockIdx.x == 0 && threadIdx.x < 4)
+    cnt->npix[threadIdx.x] = threadIdx.x == 0 ? cnt->npix_run[par] : cnt->npix_cls[par][threadIdx.x];
 }
 
 static int ccl_run(ecseg_ctx* ctx, const uint8_t* cls, int h, int w, int mode, int c, int conn8, int what, cudaStream_t st) {
-  k_ccl_tile<<<dim3(cdiv(w, kCclTile), cdiv(h, kCclTile)), 256, 0, st>>>(cls, h, w, mode, c, conn8, ctx->L, ctx->area,
-                                                                          ctx->sum_y, ctx->sum_x, ctx->flag, ctx->counters);
+  if ((size_t)cdiv(w, kCclTile) * cdiv(h, kCclTile) > ctx->max_ccl_tiles) {
+    ctx->err = "labelling: image aspect ratio needs more 32x32 tiles than the context was sized for";
+    return ECSEG_E_INVALID;
+  }
+  const int par = ctx->ccl_parity;
+  ctx->ccl_parity ^= 1;
+  const dim3 tg(cdiv(w, kCclTile), cdiv(h, kCclTile));
+#define CCL_TILE(M)                                                                                                          \
+  case M:                                                                                                                    \
+    k_ccl_tile<M><<<tg, 256, 0, st>>>(cls, h, w, c, conn8, what, par, ctx->L, ctx->area, ctx->sum_y, ctx->sum_x, ctx->flag,   \
+                                      ctx->root_list, ctx->tile_nroots, ctx->counters);                                      \
+    break;
+  switch (mode) {
+    CCL_TILE(KEY_CLASS) CCL_TILE(KEY_EQ) CCL_TILE(KEY_NE) CCL_TILE(KEY_NZ_EXCEPT) CCL_TILE(KEY_NONZERO) CCL_TILE(KEY_BITS)
+    default: ctx->err = "labelling: bad key mode"; return ECSEG_E_INVALID;
+  }
+#undef CCL_TILE
   ECSEG_CHECK_LAUNCH();
   const long long nb = (long long)((h - 1) / kCclTile) * w + (long long)((w - 1) / kCclTile) * h;
   if (nb > 0) {
     k_ccl_border<<<cdiv(nb, 256), 256, 0, st>>>(cls, h, w, mode, c, conn8, ctx->L);
     ECSEG_CHECK_LAUNCH();
   }
-  k_ccl_finish<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, mode, c, what, ctx->L, ctx->area, ctx->sum_y, ctx->sum_x,
-                                                     ctx->counters);
+  const int n_tiles = cdiv(w, kCclTile) * cdiv(h, kCclTile);
+  k_ccl_roots<<<cdiv(n_tiles, 8), 256, 0, st>>>(cls, n_tiles, mode, c, what, par, ctx->root_list, ctx->tile_nroots, ctx->L, ctx->area,
+                                                ctx->sum_y, ctx->sum_x, ctx->flag, ctx->counters);
   ECSEG_CHECK_LAUNCH();
   return ECSEG_OK;
 }
@@ -289,33 +456,23 @@ static int ccl_run(ecseg_ctx* ctx, const uint8_t* cls, int h, int w, int mode, i
 // ------------------------------------------------------------------------------------------------
 // fill_holes  (image_tools.py:36-39): complement components that do not touch the image border
 // ------------------------------------------------------------------------------------------------
-__global__ void k_mark_border(const int32_t* __restrict__ L, int h, int w, int32_t* __restrict__ flag) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int per = 2 * w + 2 * h;
-  if (t >= per) return;
-  int y, x;
-  if (t < w) { y = 0; x = t; }
-  else if (t < 2 * w) { y = h - 1; x = t - w; }
-  else if (t < 2 * w + h) { y = t - 2 * w; x = 0; }
-  else { y = t - 2 * w - h; x = w - 1; }
-  const int r = L[y * w + x];
-  if (r >= 0) flag[r] = 1;
-}
-
-__global__ void k_fill_apply(uint8_t* __restrict__ cls, int h, int w, const int32_t* __restrict__ L,
-                             const int32_t* __restrict__ flag, int c) {
-  PIXEL_XY();
-  if (x >= w) return;
-  const int i = y * w + x;
-  const int r = L[i];
-  if (r >= 0 && !flag[r]) cls[i] = (uint8_t)c;
+__global__ void __launch_bounds__(256) k_fill_apply(uint8_t* __restrict__ cls, long long n_px, const int32_t* __restrict__ L,
+                                                    const int32_t* __restrict__ flag, int c) {
+  const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * kPxPerThread;
+  Px8 p;
+  int n;
+  if (!load_px8(cls, L, n_px, i0, p, n)) return;
+  bool dirty = false;
+#pragma unroll
+  for (int k = 0; k < kPxPerThread; ++k)
+    if (k < n && p.a[k] >= 0 && !flag[L[p.a[k]]]) { p.v[k] = (uint8_t)c; dirty = true; }   // complement component off the border
+  if (dirty) store_px8(cls, i0, p, n);
 }
 
 int pp_fill_holes(ecseg_ctx* ctx, uint8_t* cls, int h, int w, int c, cudaStream_t st) {
-  ECSEG_TRY(ccl_run(ctx, cls, h, w, KEY_NE, c, /*conn8=*/0, 0, st));
-  k_mark_border<<<cdiv(2 * (h + w), 256), 256, 0, st>>>(ctx->L, h, w, ctx->flag);
-  ECSEG_CHECK_LAUNCH();
-  k_fill_apply<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, ctx->L, ctx->flag, c);
+  if (reinterpret_cast<uintptr_t>(cls) & 7) { ctx->err = "label map must be 8-byte aligned"; return ECSEG_E_INVALID; }
+  ECSEG_TRY(ccl_run(ctx, cls, h, w, KEY_NE, c, /*conn8=*/0, FIN_TOUCH, st));   // flag[root] = touches the image border
+  k_fill_apply<<<flat_blocks((long long)h * w), 256, 0, st>>>(cls, (long long)h * w, ctx->L, ctx->flag, c);
   ECSEG_CHECK_LAUNCH();
   return ECSEG_OK;
 }
@@ -323,30 +480,32 @@ int pp_fill_holes(ecseg_ctx* ctx, uint8_t* cls, int h, int w, int c, cudaStream_
 // ------------------------------------------------------------------------------------------------
 // size_thresh  (image_tools.py:41-59), all three rules from one labelling snapshot
 // ------------------------------------------------------------------------------------------------
-__global__ void k_size_apply(uint8_t* __restrict__ cls, int h, int w, const int32_t* __restrict__ L,
-                             const int32_t* __restrict__ area, const Counters* __restrict__ cnt) {
-  PIXEL_XY();
-  if (x >= w) return;
-  const int i = y * w + x;
-  const int r = L[i];
-  if (r < 0) return;
-  const int v = cls[i];
-  const long long a = area[r];
-  // `area < np.mean(areas)`  <=>  area * count < sum(areas); an empty list gives NaN -> False.
-  if (v == 1) {
-    const long long n2 = cnt->ncomp[2];
-    if (n2 > 0 && a * n2 < (long long)cnt->npix[2]) cls[i] = 0;
-  } else if (v == 2) {
-    const long long n3 = cnt->ncomp[3];
-    if (n3 > 0 && a * n3 < (long long)cnt->npix[3]) cls[i] = 3;
-  } else if (v == 3) {
-    if (a < kEcSizeThreshold) cls[i] = 0;
+__global__ void __launch_bounds__(256) k_size_apply(uint8_t* __restrict__ cls, long long n_px, const int32_t* __restrict__ L,
+                                                    const int32_t* __restrict__ area, const Counters* __restrict__ cnt) {
+  const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * kPxPerThread;
+  Px8 p;
+  int n;
+  if (!load_px8(cls, L, n_px, i0, p, n)) return;
+  const long long n2 = cnt->ncomp[2], n3 = cnt->ncomp[3];
+  const long long s2 = (long long)cnt->npix[2], s3 = (long long)cnt->npix[3];
+  bool dirty = false;
+#pragma unroll
+  for (int k = 0; k < kPxPerThread; ++k) {
+    if (k >= n || p.a[k] < 0) continue;
+    const long long a = area[L[p.a[k]]];
+    const int v = p.v[k];
+    // `area < np.mean(areas)`  <=>  area * count < sum(areas); an empty list gives NaN -> False.
+    if (v == 1) { if (n2 > 0 && a * n2 < s2) { p.v[k] = 0; dirty = true; } }
+    else if (v == 2) { if (n3 > 0 && a * n3 < s3) { p.v[k] = 3; dirty = true; } }
+    else if (v == 3) { if (a < kEcSizeThreshold) { p.v[k] = 0; dirty = true; } }
   }
+  if (dirty) store_px8(cls, i0, p, n);
 }
 
 int pp_size_thresh(ecseg_ctx* ctx, uint8_t* cls, int h, int w, cudaStream_t st) {
+  if (reinterpret_cast<uintptr_t>(cls) & 7) { ctx->err = "label map must be 8-byte aligned"; return ECSEG_E_INVALID; }
   ECSEG_TRY(ccl_run(ctx, cls, h, w, KEY_CLASS, 0, /*conn8=*/1, FIN_AREA | FIN_CLASS_PIX, st));
-  k_size_apply<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, ctx->L, ctx->area, ctx->counters);
+  k_size_apply<<<flat_blocks((long long)h * w), 256, 0, st>>>(cls, (long long)h * w, ctx->L, ctx->area, ctx->counters);
   ECSEG_CHECK_LAUNCH();
   return ECSEG_OK;
 }
@@ -354,50 +513,77 @@ int pp_size_thresh(ecseg_ctx* ctx, uint8_t* cls, int h, int w, cudaStream_t st) 
 // ------------------------------------------------------------------------------------------------
 // 3x3-cross morphology on the ecDNA mask
 // ------------------------------------------------------------------------------------------------
+// Both stencils: one thread per 4 consecutive pixels of a row (w is covered by cdiv(w, 4) threads per row), the three
+// rows are read as bytes through L1 (each byte is touched by at most 3 threads of the same or a neighbouring warp).
+#define ROW4_XY()                                                         \
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;             \
+  const int y = blockIdx.y;                                               \
+  if (x4 >= w) return;
+
+static inline dim3 row4_grid(int h, int w) { return dim3(cdiv(cdiv(w, 4), 128), h); }
+
 // image_tools.py:64: img[dilate(ec) XOR erode(ec)] = 0; erosion treats outside-image as ecDNA.
-__global__ void k_ec_boundary_erase(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int h, int w) {
-  PIXEL_XY();
-  if (x >= w) return;
-  const int i = y * w + x;
-  const uint8_t v = src[i];
-  const bool c = v == 3;
-  const bool up = y > 0 ? src[i - w] == 3 : false, dn = y < h - 1 ? src[i + w] == 3 : false;
-  const bool lf = x > 0 ? src[i - 1] == 3 : false, rt = x < w - 1 ? src[i + 1] == 3 : false;
-  const bool dil = c || up || dn || lf || rt;
-  const bool ero = c && (y > 0 ? up : true) && (y < h - 1 ? dn : true) && (x > 0 ? lf : true) && (x < w - 1 ? rt : true);
-  dst[i] = (dil != ero) ? 0 : v;
+__global__ void __launch_bounds__(128) k_ec_boundary_erase(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int h, int w) {
+  ROW4_XY();
+  const uint8_t* row = src + (size_t)y * w;
+  bool e[6];   // ec flags of x4-1 .. x4+4 in this row
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { const int x = x4 - 1 + k; e[k] = (x >= 0 && x < w) ? row[x] == 3 : false; }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = x4 + k;
+    if (x >= w) break;
+    const uint8_t v = row[x];
+    const bool c = e[k + 1], lf = e[k], rt = e[k + 2];
+    const bool up = y > 0 ? row[x - w] == 3 : false, dn = y < h - 1 ? row[x + w] == 3 : false;
+    const bool dil = c || up || dn || lf || rt;
+    const bool ero = c && (y > 0 ? up : true) && (y < h - 1 ? dn : true) && (x > 0 ? lf : true) && (x < w - 1 ? rt : true);
+    dst[(size_t)y * w + x] = (dil != ero) ? 0 : v;
+  }
 }
 
 // image_tools.py:83: img[dilate(img == 3)] = 3
-__global__ void k_ec_dilate(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int h, int w) {
-  PIXEL_XY();
-  if (x >= w) return;
-  const int i = y * w + x;
-  const uint8_t v = src[i];
-  const bool d = v == 3 || (y > 0 && src[i - w] == 3) || (y < h - 1 && src[i + w] == 3) ||
-                 (x > 0 && src[i - 1] == 3) || (x < w - 1 && src[i + 1] == 3);
-  dst[i] = d ? 3 : v;
+__global__ void __launch_bounds__(128) k_ec_dilate(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int h, int w) {
+  ROW4_XY();
+  const uint8_t* row = src + (size_t)y * w;
+  bool e[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { const int x = x4 - 1 + k; e[k] = (x >= 0 && x < w) ? row[x] == 3 : false; }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = x4 + k;
+    if (x >= w) break;
+    const bool d = e[k + 1] || e[k] || e[k + 2] || (y > 0 && row[x - w] == 3) || (y < h - 1 && row[x + w] == 3);
+    dst[(size_t)y * w + x] = d ? 3 : row[x];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // nucleus-in-metaphase removal  (image_tools.py:66-81)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_compact_centroids(const uint8_t* __restrict__ cls, int h, int w, const int32_t* __restrict__ L,
+__global__ void k_compact_centroids(const uint8_t* __restrict__ cls, int n_tiles, const int32_t* __restrict__ roots,
+                                    const int32_t* __restrict__ tile_nroots, const int32_t* __restrict__ L,
                                     const int32_t* __restrict__ area, const unsigned long long* __restrict__ sy,
                                     const unsigned long long* __restrict__ sx, double* __restrict__ ccy,
                                     double* __restrict__ ccx, int32_t* __restrict__ nuc, Counters* __restrict__ cnt) {
-  PIXEL_XY();
-  if (x >= w) return;
-  const int i = y * w + x;
-  if (L[i] != i) return;
-  const int v = cls[i];
-  if (v == 2) {
-    const int j = atomicAdd(&cnt->n_chrom, 1);
-    const double n = (double)area[i];
-    ccy[j] = __ddiv_rn((double)sy[i], n);
-    ccx[j] = __ddiv_rn((double)sx[i], n);
-  } else if (v == 1) {
-    nuc[atomicAdd(&cnt->n_nuc, 1)] = i;
+  // walks the root list of the labelling (one warp per tile), not the image
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (warp >= n_tiles) return;
+  const int n = tile_nroots[warp];
+  const int32_t* my = roots + (size_t)warp * (kCclTile * kCclTile);
+  for (int j = lane; j < n; j += 32) {
+    const int i = my[j];
+    if (L[i] != i) continue;          // a tile root that was merged into another component
+    const int v = cls[i];
+    if (v == 2) {
+      const int q = atomicAdd(&cnt->n_chrom, 1);
+      const double a = (double)area[i];
+      ccy[q] = __ddiv_rn((double)sy[i], a);
+      ccx[q] = __ddiv_rn((double)sx[i], a);
+    } else if (v == 1) {
+      nuc[atomicAdd(&cnt->n_nuc, 1)] = i;
+    }
   }
 }
 
@@ -436,23 +622,34 @@ __global__ void k_nucleus_decide(const int32_t* __restrict__ nuc, const double* 
   }
 }
 
-__global__ void k_nucleus_apply(uint8_t* __restrict__ cls, int h, int w, const int32_t* __restrict__ L,
-                                const int32_t* __restrict__ flag) {
-  PIXEL_XY();
-  if (x >= w) return;
-  const int i = y * w + x;
-  if (cls[i] == 1 && flag[L[i]]) cls[i] = 0;
+__global__ void __launch_bounds__(256) k_nucleus_apply(uint8_t* __restrict__ cls, long long n_px, const int32_t* __restrict__ L,
+                                                       const int32_t* __restrict__ flag) {
+  const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * kPxPerThread;
+  if (i0 >= n_px) return;
+  const int n = (int)min((long long)kPxPerThread, n_px - i0);
+  uint8_t v[kPxPerThread];
+  if (n == kPxPerThread) {
+    const uint2 c = *reinterpret_cast<const uint2*>(cls + i0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = (uint8_t)(c.x >> (8 * k)); v[4 + k] = (uint8_t)(c.y >> (8 * k)); }
+  } else {
+    for (int k = 0; k < n; ++k) v[k] = cls[i0 + k];
+  }
+#pragma unroll
+  for (int k = 0; k < kPxPerThread; ++k)
+    if (k < n && v[k] == 1 && flag[root_of(L, (int)(i0 + k))]) cls[i0 + k] = 0;     // nuclei are few: scattered byte stores
 }
 
 static int pp_nucleus_in_metaphase(ecseg_ctx* ctx, uint8_t* cls, int h, int w, cudaStream_t st) {
   ECSEG_TRY(ccl_run(ctx, cls, h, w, KEY_CLASS, 0, /*conn8=*/1, FIN_AREA | FIN_CENTROID, st));
-  k_compact_centroids<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, ctx->L, ctx->area, ctx->sum_y, ctx->sum_x,
-                                                            ctx->chrom_cy, ctx->chrom_cx, ctx->nuc_roots, ctx->counters);
+  const int n_tiles = cdiv(w, kCclTile) * cdiv(h, kCclTile);
+  k_compact_centroids<<<cdiv(n_tiles, 8), 256, 0, st>>>(cls, n_tiles, ctx->root_list, ctx->tile_nroots, ctx->L, ctx->area, ctx->sum_y,
+                                                        ctx->sum_x, ctx->chrom_cy, ctx->chrom_cx, ctx->nuc_roots, ctx->counters);
   ECSEG_CHECK_LAUNCH();
   k_nucleus_decide<<<296, 256, 0, st>>>(ctx->nuc_roots, ctx->chrom_cy, ctx->chrom_cx, ctx->area, ctx->sum_y,
                                         ctx->sum_x, ctx->flag, ctx->counters);
   ECSEG_CHECK_LAUNCH();
-  k_nucleus_apply<<<px_grid(h, w), px_block(), 0, st>>>(cls, h, w, ctx->L, ctx->flag);
+  k_nucleus_apply<<<flat_blocks((long long)h * w), 256, 0, st>>>(cls, (long long)h * w, ctx->L, ctx->flag);
   ECSEG_CHECK_LAUNCH();
   return ECSEG_OK;
 }
@@ -465,7 +662,7 @@ __global__ void k_mark_has_class(const uint8_t* __restrict__ cls, int h, int w, 
   PIXEL_XY();
   if (x >= w) return;
   const int i = y * w + x;
-  if (cls[i] == c) flag[L[i]] = 1;
+  if (cls[i] == c) flag[root_of(L, i)] = 1;
 }
 
 // Components (of everything but the masked class) that contain class c become all-c, except the
@@ -475,7 +672,7 @@ __global__ void k_merge_convert(uint8_t* __restrict__ cls, int h, int w, const i
   PIXEL_XY();
   if (x >= w) return;
   const int i = y * w + x;
-  const int r = L[i];
+  const int r = root_of(L, i);
   if (r >= 0 && r != cnt->last_root && flag[r]) cls[i] = (uint8_t)c;
 }
 
@@ -591,7 +788,7 @@ __global__ void k_ov_keep_large(uint8_t* __restrict__ bits, int n_px, const int3
                                 const int32_t* __restrict__ area, int min_size, int dst_bit) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_px) return;
-  const int r = L[i];
+  const int r = root_of(L, i);
   if (r >= 0 && area[r] >= min_size) bits[i] |= (uint8_t)dst_bit;
 }
 
@@ -600,7 +797,7 @@ __global__ void k_ov_flag(const uint8_t* __restrict__ other, int n_px, const int
                           int32_t* __restrict__ flag, int sel0, int sel1, int sel2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_px) return;
-  const int r = L[i];
+  const int r = root_of(L, i);
   if (r < 0) return;
   const uint8_t v = other[i];
   int f = 0;
@@ -711,7 +908,7 @@ int pp_remove_small_objects(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w,
 // ------------------------------------------------------------------------------------------------
 __global__ void k_label_export(const int32_t* __restrict__ L, int n, int32_t* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = L[i] + 1;
+  if (i < n) out[i] = root_of(L, i) + 1;
 }
 
 int pp_label(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w, int conn, int32_t* d_out, cudaStream_t st) {
@@ -731,18 +928,19 @@ int pp_postprocess(ecseg_ctx* ctx, uint8_t* cls, int h, int w, int flags, int32_
     ctx->err = "ecseg_postprocess: image larger than the context's max_h x max_w";
     return ECSEG_E_INVALID;
   }
+  if (reinterpret_cast<uintptr_t>(cls) & 7) { ctx->err = "ecseg_postprocess: label map must be 8-byte aligned"; return ECSEG_E_INVALID; }
   uint8_t* t = ctx->tmp_a;
   ECSEG_TRY(pp_fill_holes(ctx, cls, h, w, 1, st));                       // :61
   ECSEG_TRY(pp_fill_holes(ctx, cls, h, w, 2, st));                       // :61
   ECSEG_TRY(pp_size_thresh(ctx, cls, h, w, st));                         // :62
-  k_ec_boundary_erase<<<px_grid(h, w), px_block(), 0, st>>>(cls, t, h, w);  // :64   cls -> t
+  k_ec_boundary_erase<<<row4_grid(h, w), 128, 0, st>>>(cls, t, h, w);  // :64   cls -> t
   ECSEG_CHECK_LAUNCH();
   ECSEG_TRY(pp_nucleus_in_metaphase(ctx, t, h, w, st));                  // :66-81
   if (flags & ECSEG_PP_FAITHFUL_MERGE) {                                 // :82 (no-op here)
     ECSEG_TRY(pp_merge_comp(ctx, t, h, w, 1, st));
     ECSEG_TRY(pp_merge_comp(ctx, t, h, w, 2, st));
   }
-  k_ec_dilate<<<px_grid(h, w), px_block(), 0, st>>>(t, cls, h, w);       // :83   t -> cls
+  k_ec_dilate<<<row4_grid(h, w), 128, 0, st>>>(t, cls, h, w);       // :83   t -> cls
   ECSEG_CHECK_LAUNCH();
   if (d_n_ec || d_ec_px) ECSEG_TRY(count_mode(ctx, cls, h, w, KEY_EQ, 3, d_n_ec, d_ec_px, st));  // metaseg.py:46
   return ECSEG_OK;

@@ -49,12 +49,19 @@ def write_csv(csv_path: str, rows: Sequence[tuple[str, int]]) -> None:
 
 
 def run_sharded(image_paths: Sequence[str], process_one: Callable[[str], int], rank: int, world: int,
-                gather: Callable[[list], list | None]) -> list[tuple[str, int]] | None:
-    """Process this rank's share with `process_one(path) -> ecDNA count`, gather the rows with
+                gather: Callable[[list], list | None],
+                process_batch: Callable[[list], list] | None = None) -> list[tuple[str, int]] | None:
+    """Process this rank's share with `process_one(path) -> ecDNA count` (or, when given, the whole share at once
+    with `process_batch(paths) -> counts`, which lets decode / GPU / writes overlap), gather the rows with
     `gather(rows)` (returns the list of all ranks' rows on rank 0, None elsewhere) and merge."""
-    mine = []
-    for i in shard_indices(len(image_paths), rank, world):
-        mine.append((i, os.path.split(image_paths[i])[1], int(process_one(image_paths[i]))))
+    idx = shard_indices(len(image_paths), rank, world)
+    if process_batch is not None:
+        counts = list(process_batch([image_paths[i] for i in idx]))
+        if len(counts) != len(idx):
+            raise ValueError("process_batch must return one count per path")
+    else:
+        counts = [process_one(image_paths[i]) for i in idx]
+    mine = [(i, os.path.split(image_paths[i])[1], int(n)) for i, n in zip(idx, counts)]
     everyone = gather(mine)
     if everyone is None:
         return None
@@ -114,7 +121,25 @@ def main(argv=None) -> int:
         np.save(out, I)
         return model.last_count
 
-    rows = run_sharded(paths, process_one, rank, world, lambda r: dist_gather(r, rank, world))
+    def process_batch(mine: list) -> list:
+        """This rank's share: *.tif through the overlapped pipeline on this GPU, anything else one by one."""
+        tifs = [p for p in mine if p.lower().endswith('.tif')]
+        counts = {}
+        if tifs and not os.environ.get("ECSEG_SERIAL"):
+            from . import tiffio
+            from .pipeline import FilesPipeline
+            shapes = [tiffio.probe(p) or ms._shape_of(p) for p in tifs]
+            pipe = FilesPipeline(model.weights, model.precision, max(max(s[0] for s in shapes), 256),
+                                 max(max(s[1] for s in shapes), 256), device=local, n_ctx=int(var.get('contexts', 2)),
+                                 n_readers=int(var.get('readers', 4)), n_writers=int(var.get('writers', 6)),
+                                 max_bytes_per_px=max(s[2] * s[3] for s in shapes))
+            try:
+                counts.update(dict(pipe.run(tifs)))
+            finally:
+                pipe.close()
+        return [counts[p] if p in counts else process_one(p) for p in mine]
+
+    rows = run_sharded(paths, process_one, rank, world, lambda r: dist_gather(r, rank, world), process_batch)
     if rows is not None:
         csv_path = os.path.join(inpath, 'ec_quantification.csv')
         print("Saving ec quantification to", csv_path)

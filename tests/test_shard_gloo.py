@@ -72,3 +72,26 @@ def test_world2_gloo_csv_equals_single_process(tmp_path):
     lines = ref_csv.read_text().splitlines()
     assert lines[0] == "image name,# of ec" and len(lines) == 1 + len(paths)
     assert lines[-1].startswith('"odd,name ""x"".tif",')
+
+
+def test_process_batch_share_and_length_check():
+    """The per-rank batch hook (the overlapped file pipeline on a GPU box) sees exactly this rank's share, in order."""
+    paths = [f"/d/i{i}.tif" for i in range(9)]
+    for world in (1, 2, 4):
+        per_rank = []
+        for rank in range(world):
+            seen = []
+
+            def batch(mine):
+                seen.extend(mine)
+                return [fake_count(p) for p in mine]
+
+            def gather(rows):
+                per_rank.append(rows)
+                return None           # what every rank but 0 sees
+
+            assert shard.run_sharded(paths, fake_count, rank, world, gather, batch) is None
+            assert seen == paths[rank::world]
+        assert shard.merge_rows(per_rank, 9) == [(os.path.basename(p), fake_count(p)) for p in paths]
+    with pytest.raises(ValueError):
+        shard.run_sharded(paths, fake_count, 0, 1, lambda r: [r], lambda mine: [1])
