@@ -56,8 +56,15 @@ def load_model(model_name: str, precision: str | None = None) -> MetasegModel:
     redistributable offline) and a notice is printed."""
     precision = precision or os.environ.get("ECSEG_PRECISION", "fp16")
     path = wmod.default_weights_path(model_name)
+    h5 = os.path.join("models", model_name)
     if os.path.isfile(path):
         w = wmod.load_npz(path)
+    elif model_name.endswith(".h5") and os.path.isfile(h5):
+        # the reference's own checkpoint: discover its architecture, map the weights, keep the .npz next to it
+        from . import keras_import
+        w = keras_import.load_keras_h5(h5)          # ImportError (h5py) / ArchitectureMismatch propagate loudly
+        wmod.save_npz(path, w)
+        print(f"[ecseg_b200] imported {h5} -> {path}")
     else:
         print(f"[ecseg_b200] {path} not found: using seeded random-init weights of the metaseg architecture")
         w = wmod.make_weights(0)
