@@ -57,6 +57,7 @@ SIGNATURES = {
     "ecseg_crc32": (ctypes.c_uint32, [ctypes.c_uint32, c_void_p, c_size_t]),
     "ecseg_debug_layer_output": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ecseg_debug_set": (c_int, [c_void_p, c_int, c_int, c_int]),
+    "ecseg_debug_progress": (c_int, [c_void_p, c_void_p]),
     "ecseg_device_error": (c_int, [c_void_p, POINTER(c_int)]),
     "ecseg_launch_count": (c_int64, [c_void_p]),
     "ecseg_last_stage_ms": (c_int, [c_void_p, POINTER(c_float)]),

@@ -401,6 +401,15 @@ int ecseg_debug_set(ecseg_ctx* ctx, int stop_after_layer, int tc_cluster, int tc
   return unet_set_debug(ctx, stop_after_layer, tc_cluster, tc_ntile_max);
 }
 
+int ecseg_debug_progress(ecseg_ctx* ctx, int32_t out[8]) {
+  API_GUARD(ctx);
+  static cudaStream_t side = nullptr;     // non-blocking: readable while a kernel of the context is still running
+  if (!side) ECSEG_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+  ECSEG_CUDA(cudaMemcpyAsync(out, ctx->counters->progress, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, side));
+  ECSEG_CUDA(cudaStreamSynchronize(side));
+  return ECSEG_OK;
+}
+
 int ecseg_device_error(ecseg_ctx* ctx, int* code) {
   API_GUARD(ctx);
   ECSEG_CUDA(cudaDeviceSynchronize());

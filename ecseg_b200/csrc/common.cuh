@@ -35,6 +35,7 @@ struct Counters {
   int range_error;                 // img_as_ubyte range violation seen
   int device_error;                // tcgen05 pipeline watchdog
   int ov_hits[4];                  // meta_overlay: components flagged per colocalisation test
+  int progress[8];                 // tcgen05 pipeline progress markers (ecseg_debug_progress; written by one thread per role)
   // per labelling run, double buffered by run parity (a run clears the other parity's slots for the next run)
   unsigned long long npix_run[2];  // foreground pixels
   unsigned long long npix_cls[2][4];  // pixels per class value

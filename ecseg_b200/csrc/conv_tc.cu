@@ -46,6 +46,22 @@ constexpr int kPoolStage = 32 * 128;               // pooled staging tile: 32 pi
 constexpr int kMaxBars = 32;
 constexpr int kMaxCout = 1024;
 
+// conv1-1 fused into conv1-2 (FUSE1): instead of a TMA load, a halo stage is PRODUCED in place by four extra warps.
+// conv1-1 (Cin = 1, 9 taps) runs as an im2col GEMM on the tensor core: A1 = [384 halo pixels (324 used) x K=32]
+// (the 9 taps twice, zero padded) built from the 20x20 uint8 input patch, B1 = [64 x 32] weights split into a high and
+// a low 16-bit half (w = hi + lo, so the fp32-accumulated product carries ~22 weight bits: the layer loses nothing
+// against the fp32 CUDA-core version it replaces), 3 x 2 M=128 MMAs into a private TMEM region; the generator warps read it back, add bias, ReLU, zero the pixels outside the tile (Keras
+// 'same' padding of conv1-2) and store 16-bit rows into the halo stage with the TMA's 128-byte swizzle.  The
+// 839 MB conv1-1 activation never exists in HBM.
+constexpr int kGenThreads = 128;
+constexpr int kGenWarp0 = 12;
+constexpr int kGenA1Bytes = 384 * 128;           // im2col rows padded to 128 B (SWIZZLE_128B, only k = 0..15 used)
+constexpr int kGenB1Bytes = 64 * 128;
+constexpr int kGenMiscBytes = 1024;              // [0,400) input patch, [512, 768) conv1-1 bias
+constexpr int kGenBytes = kGenA1Bytes + kGenB1Bytes + kGenMiscBytes;
+constexpr int kGenTmemCol = 256;                 // behind the two conv1-2 accumulator stages (2 x 128 columns)
+constexpr int kHaloPixels = 18 * 18;
+
 // Transposed conv: the 9 taps grouped by the halo view (dy, dx) they read.  acc' = px*2 + py is the accumulator
 // (output parity) a tap feeds; taps of one view sit in consecutive 8 KB slots of one weight stage so that
 // accumulators that are adjacent in TMEM are covered by ONE wider MMA:
@@ -64,13 +80,14 @@ __device__ constexpr int kViewTap[kNumViews][4] = {{0, 3, 1, 4}, {2, 5, 0, 0}, {
 __host__ __device__ constexpr int b_stage_bytes(int n_tile, int nacc, bool pair) {
   return (nacc == 4 ? 4 * n_tile * 128 : n_tile * 128) / (pair ? 2 : 1);
 }
-__host__ __device__ constexpr int smem_bytes(int n_tile, int nacc, bool pair, int a_stages, int b_stages) {
-  return a_stages * kAStride + b_stages * b_stage_bytes(n_tile, nacc, pair) + 2 * kOutStage + 2 * kPoolStage + kMaxCout * 4 +
-         kMaxBars * 8 + 16 + 1024;
+__host__ __device__ constexpr int smem_bytes(int n_tile, int nacc, bool pair, int a_stages, int b_stages, bool fuse1 = false) {
+  return a_stages * kAStride + b_stages * b_stage_bytes(n_tile, nacc, pair) + (fuse1 ? kGenBytes : 0) + 2 * kOutStage +
+         2 * kPoolStage + kMaxCout * 4 + kMaxBars * 8 + 16 + 1024;
 }
 
-template <int N_TILE, int NACC, int CS, bool PAIR>
-__global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__ ConvTcParams p) {
+template <int N_TILE, int NACC, int CS, bool PAIR, bool FUSE1>
+__global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) k_conv_tc(const __grid_constant__ ConvTcParams p) {
+  static_assert(!FUSE1 || (N_TILE == 64 && NACC == 1 && CS == 1 && !PAIR), "conv1-1 fusion is built for the conv1-2 configuration");
   constexpr int kBBytes = N_TILE * 128;                 // one tap's weight tile
   constexpr int kBStage = b_stage_bytes(N_TILE, NACC, PAIR);  // conv: one tap; transposed conv: one view (up to 4 taps)
   constexpr int kAccCols = 2 * NACC * N_TILE;
@@ -85,9 +102,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
   const int AS = p.a_stages, BS = p.b_stages;
   const uint32_t a_base = smem_u32(smem);
   const uint32_t b_base = a_base + AS * kAStride;
-  const uint32_t o_base = b_base + BS * kBStage;                 // 2 output staging tiles (one per epilogue group)
+  constexpr int kGen = FUSE1 ? kGenBytes : 0;
+  const uint32_t g_a1 = b_base + BS * kBStage;                   // FUSE1: im2col operand, weights, patch + bias
+  const uint32_t g_b1 = g_a1 + kGenA1Bytes;
+  const uint32_t g_misc = g_b1 + kGenB1Bytes;
+  const uint32_t o_base = b_base + BS * kBStage + kGen;          // 2 output staging tiles (one per epilogue group)
   const uint32_t q_base = o_base + 2 * kOutStage;                // 2 pooled staging tiles
-  float* s_bias = reinterpret_cast<float*>(smem + AS * kAStride + BS * kBStage + 2 * kOutStage + 2 * kPoolStage);
+  float* s_bias = reinterpret_cast<float*>(smem + AS * kAStride + BS * kBStage + kGen + 2 * kOutStage + 2 * kPoolStage);
   const uint32_t s_bias_u32 = q_base + 2 * kPoolStage;
   const uint32_t bar_base = s_bias_u32 + kMaxCout * 4;
   auto full_a = [&](int s) { return bar_base + 8u * s; };
@@ -96,7 +117,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
   auto empty_b = [&](int s) { return bar_base + 8u * (2 * AS + BS + s); };
   auto tmem_full = [&](int s) { return bar_base + 8u * (2 * AS + 2 * BS + s); };
   auto tmem_empty = [&](int s) { return bar_base + 8u * (2 * AS + 2 * BS + 2 + s); };
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + AS * kAStride + BS * kBStage + 2 * kOutStage +
+  const uint32_t gen_done = bar_base + 8u * (2 * AS + 2 * BS + 4);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + AS * kAStride + BS * kBStage + kGen + 2 * kOutStage +
                                                         2 * kPoolStage + kMaxCout * 4 + kMaxBars * 8);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
@@ -107,6 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     for (int s = 0; s < AS; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
     for (int s = 0; s < BS; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), PAIR ? 1 : CS); }
     for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), PAIR ? 512 : 256); }
+    if (FUSE1) mbar_init(gen_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
     if (PAIR) tmem_alloc_2sm(smem_u32(tmem_ptr_smem), kTmemCols);
@@ -118,7 +141,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
   }
   {
     const int cout = p.n_chunks * N_TILE;
-    for (int i = threadIdx.x; i < cout; i += kThreads) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < cout; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+  }
+  if (FUSE1 && warp >= kGenWarp0) {
+    // conv1-1 weights [64 cout][32 k] 16-bit -> K-major SWIZZLE_128B rows (four 16-byte chunks per row); fp32 bias
+    const int t = threadIdx.x - kGenWarp0 * 32;
+#pragma unroll
+    for (int e = t; e < 64 * 4; e += kGenThreads) {
+      const int row = e >> 2, j = e & 3;
+      const uint4 v = reinterpret_cast<const uint4*>(p.first_w)[row * 4 + j];
+      st_shared_v4(g_b1 + (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4), v);
+    }
+    if (t == 0) *reinterpret_cast<volatile int*>(smem + (g_misc - a_base) + 768) = 0;     // generator failure flag
+    fence_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -126,6 +161,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem), 0);
 
+  auto mark = [&](int slot, int v) {
+    if (p.progress && blockIdx.x == 0) *reinterpret_cast<volatile int*>(p.progress + slot) = v;
+  };
   const int bw = p.W >> 4, bh = p.H >> 4;
   const int n_mblocks = p.n_img * bh * bw;
   const int n_mgroups = (n_mblocks + CS - 1) / CS;
@@ -147,9 +185,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
       const int img = mb / (bh * bw), rem = mb % (bh * bw);
       const int y0 = (rem / bw) << 4, x0 = (rem % bw) << 4;
       for (int ch = 0; ch < p.cin_chunks && ok; ++ch) {
-        ok = __all_sync(0xffffffffu, mbar_wait(empty_a(sa), pa ^ 1, p.device_error, 1));
+        if (!FUSE1) ok = __all_sync(0xffffffffu, mbar_wait(empty_a(sa), pa ^ 1, p.device_error, 1));
         if (!ok) break;
-        if (leader) {
+        if (FUSE1) {
+          // the halo stage is produced by the generator warps
+        } else if (leader) {
           if (PAIR) {   // both CTAs' halos complete on the leader CTA's barrier
             if (rank == 0) mbar_expect_tx(full_a(sa), 2 * kABytes);
             tma_load_4d_2sm(a_base + sa * kAStride, &p.tm_a, full_a(sa), ch * 64, x0 - 1, y0 - 1, img);
@@ -178,6 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
               }
             }
             if (++sb == BS) { sb = 0; pb ^= 1; }
+            if (leader) mark(0, it * 16 + t + 1);
           }
         } else {
 #pragma unroll
@@ -315,8 +356,136 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         if (++sa == AS) { sa = 0; pa ^= 1; }
       }
       if (leader) commit_all(tmem_full(as), /*local_only=*/true);     // accumulators complete -> epilogue
+      if (leader) mark(1, it + 1);
       __syncwarp();
       if (++as == kAccStages) { as = 0; pacc ^= 1; }
+    }
+  } else if (FUSE1 && warp >= kGenWarp0) {
+    // ===================== conv1-1 generator (FUSE1) =====================
+    const int t = threadIdx.x - kGenWarp0 * 32;           // 0..127 = TMEM lane = row of an M=128 tile
+    const int q = warp & 3;
+    const uint8_t* s_patch = smem + (g_misc - a_base);
+    const uint32_t idesc1 = make_idesc(128, 64, p.is_bf16);
+    const uint32_t hi1 = sdesc_hi(1024);
+    const uint32_t t1 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)kGenTmemCol;
+    auto item_origin = [&](int it, int& img, int& y0, int& x0) {
+      int mb = it % n_mgroups;
+      if (mb >= n_mblocks) mb = n_mblocks - 1;
+      img = mb / (bh * bw);
+      const int rem = mb % (bh * bw);
+      y0 = (rem / bw) << 4; x0 = (rem % bw) << 4;
+    };
+    // input byte e of the 20x20 patch around block (y0, x0) of tile `img`; zero outside the tile ('same' padding of conv1-1)
+    auto patch_byte = [&](int img, int y0, int x0, int e) -> uint8_t {
+      const int yy = y0 - 2 + e / 20, xx = x0 - 2 + e % 20;
+      if (e >= 400 || yy < 0 || yy >= kTile || xx < 0 || xx >= kTile) return 0;
+      if (p.first_from_tiles) return p.first_src[((size_t)img * kTile + yy) * kTile + xx];
+      const int ri = img % p.first_grid.nr, ci = img / p.first_grid.nr;
+      return p.first_src[(size_t)(p.first_grid.start_r(ri) + yy) * p.first_grid.w + p.first_grid.start_c(ci) + xx];
+    };
+    uint8_t pre[4] = {0, 0, 0, 0};
+    if (cluster_id < n_items) {
+      int img, y0, x0;
+      item_origin(cluster_id, img, y0, x0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pre[k] = patch_byte(img, y0, x0, t + kGenThreads * k);
+    }
+    int sa = 0, pa = 0, pg = 0;
+    bool ok = true;
+    for (int it = cluster_id; it < n_items && ok; it += n_clusters) {
+      int img, y0, x0;
+      item_origin(it, img, y0, x0);
+      // the previous item's patch / im2col readers are done (its MMAs completed before gen_done fired)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (t + kGenThreads * k < 400) const_cast<uint8_t*>(s_patch)[t + kGenThreads * k] = pre[k];
+      named_bar_sync(5, kGenThreads);
+      if (t == 0) mark(3, it * 8 + 1);
+      if (it + n_clusters < n_items) {          // prefetch the next item's patch: its latency hides behind this item
+        int im2, y2, x2;
+        item_origin(it + n_clusters, im2, y2, x2);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pre[k] = patch_byte(im2, y2, x2, t + kGenThreads * k);
+      }
+      // im2col rows: halo pixel pix = mt*128 + t -> taps (ky, kx) at patch[(hy + ky) * 20 + hx + kx]
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt) {
+        const int pix = mt * 128 + t;
+        if (pix < kHaloPixels) {
+          const int hy = pix / 18, hx = pix % 18;
+          float v[9];
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) v[ky * 3 + kx] = (float)s_patch[(hy + ky) * 20 + hx + kx];
+          uint4 c0, c1;
+          c0.x = pack2(v[0], v[1], p.is_bf16); c0.y = pack2(v[2], v[3], p.is_bf16);
+          c0.z = pack2(v[4], v[5], p.is_bf16); c0.w = pack2(v[6], v[7], p.is_bf16);
+          c1.x = pack2(v[8], 1.f, p.is_bf16); c1.y = 0u; c1.z = 0u; c1.w = 0u;     // k = 9: ones column, meets the bias row
+          // k = 0..15 meets the high halves of the weights, k = 16..31 the same taps again for the low halves
+          const uint32_t rowa = g_a1 + (uint32_t)pix * 128u;
+          st_shared_v4(rowa + (uint32_t)((0 ^ (pix & 7)) << 4), c0);
+          st_shared_v4(rowa + (uint32_t)((1 ^ (pix & 7)) << 4), c1);
+          st_shared_v4(rowa + (uint32_t)((2 ^ (pix & 7)) << 4), c0);
+          st_shared_v4(rowa + (uint32_t)((3 ^ (pix & 7)) << 4), c1);
+        }
+      }
+      fence_async_smem();
+      named_bar_sync(5, kGenThreads);
+      if (t == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_f16(tmem_base + (uint32_t)(kGenTmemCol + mt * 64),
+                     sdesc_join(sdesc_lo(g_a1 + (uint32_t)(mt * 128 * 128)) + k * 2, hi1), sdesc_join(sdesc_lo(g_b1) + k * 2, hi1),
+                     idesc1, (uint32_t)k);
+        umma_commit(gen_done);
+        mark(3, it * 8 + 2);
+      }
+      // the halo stage must be free before it is overwritten
+      // (a failed wait must take all four warps out together: the named barriers below have no time-out)
+      volatile int* s_fail = reinterpret_cast<volatile int*>(smem + (g_misc - a_base) + 768);
+      if (!(mbar_wait<64>(empty_a(sa), pa ^ 1, p.device_error, 7) && mbar_wait<64>(gen_done, pg, p.device_error, 8))) *s_fail = 1;
+      named_bar_sync(5, kGenThreads);
+      ok = *s_fail == 0;
+      if (!ok) break;
+      pg ^= 1;
+      tc_fence_after();
+      if (t == 0) mark(3, it * 8 + 3);
+      const uint32_t stage = a_base + sa * kAStride;
+#pragma unroll 1
+      for (int mt = 0; mt < 3; ++mt) {
+        const int pix = mt * 128 + t;
+        const int hy = pix / 18, hx = pix % 18;
+        const int yy = y0 - 1 + hy, xx = x0 - 1 + hx;
+        const bool inside = pix < kHaloPixels && yy >= 0 && yy < kTile && xx >= 0 && xx < kTile;
+        const uint32_t rowo = stage + (uint32_t)pix * 128u;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t v[32];
+          tmem_ld32(t1 + (uint32_t)(mt * 64 + cc * 32), v);
+          tmem_ld_wait();
+          if (pix < kHaloPixels) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              uint4 o;      // bias came through the GEMM; ReLU (models.py:20); pixels outside the tile are conv1-2's zero padding
+              o.x = pack2(fmaxf(__uint_as_float(v[8 * k]), 0.f), fmaxf(__uint_as_float(v[8 * k + 1]), 0.f), p.is_bf16);
+              o.y = pack2(fmaxf(__uint_as_float(v[8 * k + 2]), 0.f), fmaxf(__uint_as_float(v[8 * k + 3]), 0.f), p.is_bf16);
+              o.z = pack2(fmaxf(__uint_as_float(v[8 * k + 4]), 0.f), fmaxf(__uint_as_float(v[8 * k + 5]), 0.f), p.is_bf16);
+              o.w = pack2(fmaxf(__uint_as_float(v[8 * k + 6]), 0.f), fmaxf(__uint_as_float(v[8 * k + 7]), 0.f), p.is_bf16);
+              if (!inside) o = make_uint4(0u, 0u, 0u, 0u);
+              st_shared_v4(rowo + (uint32_t)(((cc * 4 + k) ^ (pix & 7)) << 4), o);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      fence_async_smem();
+      named_bar_sync(5, kGenThreads);
+      if (t == 0) { mbar_arrive(full_a(sa)); mark(3, it * 8 + 4); }
+      if (++sa == AS) { sa = 0; pa ^= 1; }
     }
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue =====================
@@ -342,7 +511,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
       const int mb = ghost ? n_mblocks - 1 : mb_raw;
       const int img = mb / (bh * bw), rem = mb % (bh * bw);
       const int y0 = (rem / bw) << 4, x0 = (rem % bw) << 4;
-      ok = mbar_wait(tmem_full(as), pacc, p.device_error, 6);
+      ok = mbar_wait<64>(tmem_full(as), pacc, p.device_error, 6);
       if (!ok) break;
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccCols);
@@ -417,6 +586,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         }
       }
       tc_fence_before();
+      if (e0 && eg == 0) mark(2, it + 1);
       if (PAIR) mbar_arrive_cluster(tmem_empty(as), 0);   // the leader's MMA warp waits for both CTAs' epilogues
       else mbar_arrive(tmem_empty(as));
       if (++as == kAccStages) { as = 0; pacc ^= 1; }
@@ -434,16 +604,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
   }
 }
 
-template <int N_TILE, int NACC, int CS, bool PAIR>
+template <int N_TILE, int NACC, int CS, bool PAIR, bool FUSE1 = false>
 int launch_cfg(ecseg_ctx* ctx, ConvTcParams& p, cudaStream_t st) {
-  auto kern = k_conv_tc<N_TILE, NACC, CS, PAIR>;
+  auto kern = k_conv_tc<N_TILE, NACC, CS, PAIR, FUSE1>;
   // pipeline depths: halo stages first (each covers 9 taps of MMA work), the rest goes to weight stages
   const int budget = 227 * 1024;
-  p.a_stages = (N_TILE == 64 && NACC == 1) ? 3 : 2;
-  p.b_stages = (budget - smem_bytes(N_TILE, NACC, PAIR, p.a_stages, 0)) / b_stage_bytes(N_TILE, NACC, PAIR);
+  p.a_stages = (N_TILE == 64 && NACC == 1 && !FUSE1) ? 3 : 2;
+  p.b_stages = (budget - smem_bytes(N_TILE, NACC, PAIR, p.a_stages, 0, FUSE1)) / b_stage_bytes(N_TILE, NACC, PAIR);
   if (p.b_stages > 8) p.b_stages = 8;
-  if (p.b_stages < 2 || 2 * p.a_stages + 2 * p.b_stages + 4 > kMaxBars) { ctx->err = "conv_tc: bad pipeline configuration"; return ECSEG_E_INVALID; }
-  const int smem = smem_bytes(N_TILE, NACC, PAIR, p.a_stages, p.b_stages);
+  if (p.b_stages < 2 || 2 * p.a_stages + 2 * p.b_stages + 5 > kMaxBars) { ctx->err = "conv_tc: bad pipeline configuration"; return ECSEG_E_INVALID; }
+  const int smem = smem_bytes(N_TILE, NACC, PAIR, p.a_stages, p.b_stages, FUSE1);
   static bool attr_done = false;
   if (!attr_done) {
     ECSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
@@ -456,7 +626,7 @@ int launch_cfg(ecseg_ctx* ctx, ConvTcParams& p, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(clusters * CS);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(FUSE1 ? kThreads + kGenThreads : kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -488,6 +658,13 @@ int conv_tc_launch(ecseg_ctx* ctx, ConvTcParams& p, int n_tile, int cluster, cud
     return ECSEG_E_INVALID;
   }
   // cluster: 1 = single CTAs, 2 = CTA clusters sharing weight tiles by TMA multicast, 3 = CTA pairs (cta_group::2 MMA)
+  if (p.first_src) {
+    if (p.n_acc != 1 || n_tile != 64 || p.cin_chunks != 1 || p.n_chunks != 1 || !p.first_w || !p.first_bias) {
+      ctx->err = "conv_tc: the conv1-1 fusion needs the conv1-2 configuration (64 -> 64 channels)";
+      return ECSEG_E_INVALID;
+    }
+    return launch_cfg<64, 1, 1, false, true>(ctx, p, st);
+  }
   if (p.n_acc == 1) {
     if (cluster == 3) return launch_n<1, 2, true>(ctx, p, n_tile, st);
     return cluster == 2 ? launch_n<1, 2, false>(ctx, p, n_tile, st) : launch_n<1, 1, false>(ctx, p, n_tile, st);

@@ -36,6 +36,15 @@ struct ConvTcParams {
   int has_pool;
   int a_stages, b_stages; // shared-memory pipeline depths chosen by the host
   int* device_error;      // watchdog flag (Counters::device_error)
+  int* progress;          // Counters::progress (nullable): role progress markers of CTA 0 for ecseg_debug_progress
+  // conv1-1 fused in front of this layer (conv1-2 only; first_src == nullptr: off).  The halo stages are then computed
+  // in the kernel from the uint8 input (materialised tiles, or the pre-processed image through the tile grid) and
+  // tm_a is unused.
+  const uint8_t* first_src;
+  int first_from_tiles;
+  TileGrid first_grid;
+  const void* first_w;      // [64 cout][32 k] 16-bit: k = tap (hi half of the weight), 16 + tap (lo half), zero elsewhere
+  const float* first_bias;  // [64] fp32
 };
 
 // n_tile in {64, 128, 256}; cluster in {1, 2}: CTAs of a cluster share every weight tile through TMA multicast.

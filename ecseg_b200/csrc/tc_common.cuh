@@ -21,23 +21,31 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// try_wait with a suspend-time hint: the waiting thread is parked by the hardware until the phase completes (or the
+// hint expires) instead of spinning.  Without it, the ~10 waiting warps of a CTA burned half of the SM's issue slots
+// in try_wait loops and slowed the warps that had work (profiles/r01_ncu_fuse1.md).
+constexpr uint32_t kSuspendHintNs = 1000000u;
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(kSuspendHintNs)
       : "memory");
   return ok;
 }
 // Bounded wait: returns false (and raises the device error flag) instead of hanging forever.
+// BACKOFF_NS > 0: sleep between polls -- for the many-thread roles (epilogue, generator) whose polling would otherwise
+// take issue slots from the warps that share their scheduler and have work.
+template <int BACKOFF_NS = 0>
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
   if (mbar_try_wait(bar, parity)) return true;
   const long long t0 = clock64();
   unsigned spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (BACKOFF_NS > 0) __nanosleep(BACKOFF_NS);
     if ((++spins & 255u) == 0) {
       if (clock64() - t0 > kWatchdogCycles || *(volatile int*)err_flag != 0) {
         atomicCAS(err_flag, 0, code);

@@ -64,6 +64,11 @@ struct UNet {
   // tcgen05 knobs (ECSEG_TC_CLUSTER / ECSEG_TC_NTILE_MAX env overrides)
   int tc_cluster = 0, tc_ntile_max = 0;   // 0 = per-layer table
   int stop_after = -1;   // debug: stop the forward after this layer
+  // conv1-1 fused into conv1-2's halo producer (tensor-core modes; ECSEG_NO_FUSE_FIRST=1 or a debug stop disables it)
+  void* w_first16 = nullptr;          // [64][32] 16-bit conv1-1 weights, k = tap (hi half), 16 + tap (lo half)
+  int fuse_first = 1;
+  const uint8_t* in_tiles = nullptr;  // inputs of the forward in flight (read by the fused first layer)
+  const uint8_t* in_pre = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -351,6 +356,7 @@ int unet_create(ecseg_ctx* ctx) {
   ctx->net = new UNet();
   if (const char* e = getenv("ECSEG_TC_CLUSTER")) { const int v = atoi(e); if (v >= 1 && v <= 3) ctx->net->tc_cluster = v; }
   if (const char* e = getenv("ECSEG_TC_NTILE_MAX")) ctx->net->tc_ntile_max = atoi(e);
+  if (const char* e = getenv("ECSEG_NO_FUSE_FIRST")) ctx->net->fuse_first = atoi(e) ? 0 : 1;
   return ECSEG_OK;
 }
 
@@ -362,6 +368,7 @@ static void free_net_buffers(UNet* n) {
     n->w[l] = nullptr; n->b[l] = nullptr;
   }
   if (n->debug_dump) { cudaFree(n->debug_dump); n->debug_dump = nullptr; }
+  if (n->w_first16) { cudaFree(n->w_first16); n->w_first16 = nullptr; }
 }
 
 void unet_destroy(ecseg_ctx* ctx) {
@@ -431,6 +438,27 @@ int unet_load_weights(ecseg_ctx* ctx, const float* blob, size_t n_floats, int pr
       ECSEG_CUDA(cudaMalloc(&net->w[li], w.size() * sizeof(float)));
       ECSEG_CUDA(cudaMemcpy(net->w[li], w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
       net->cout_rows[li] = 64;
+      if (tc) {      // the same weights as a [64 cout][32 k] 16-bit GEMM operand (hi | lo halves) for the fused first layer
+        std::vector<uint16_t> w16(64 * 32, 0);
+        auto h2f = [&](uint16_t u) -> float {
+          if (bf16) { __nv_bfloat16 h; memcpy(&h, &u, 2); return __bfloat162float(h); }
+          __half h; memcpy(&h, &u, 2); return __half2float(h);
+        };
+        for (int co = 0; co < 64; ++co)
+          for (int t = 0; t < 9; ++t) {
+            const float wv = kval(t, 0, co);
+            const uint16_t hi = f2h_bits(wv, bf16);
+            w16[co * 32 + t] = hi;
+            w16[co * 32 + 16 + t] = f2h_bits(wv - h2f(hi), bf16);
+          }
+        for (int co = 0; co < 64; ++co) {      // k = 9 / 25: the folded bias, hi | lo, met by a column of ones
+          const uint16_t hi = f2h_bits(fb[co], bf16);
+          w16[co * 32 + 9] = hi;
+          w16[co * 32 + 16 + 9] = f2h_bits(fb[co] - h2f(hi), bf16);
+        }
+        ECSEG_CUDA(cudaMalloc(&net->w_first16, w16.size() * 2));
+        ECSEG_CUDA(cudaMemcpy(net->w_first16, w16.data(), w16.size() * 2, cudaMemcpyHostToDevice));
+      }
     } else if (tc && li == 22) {   // head: [48][64] 16-bit, row = tap*4 + class (head_tc.cu)
       std::vector<uint16_t> w((size_t)48 * l.cin, 0);
       for (int t = 0; t < 9; ++t)
@@ -552,6 +580,8 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   if (li == 1 || li == 2 || li == 19) cs = 2;       // conv1-2, conv2-1, up1
   if (net->tc_ntile_max > 0 && !l.convT) n_tile = rows < net->tc_ntile_max ? rows : net->tc_ntile_max;   // debug override
   if (net->tc_cluster > 0) cs = net->tc_cluster;                                                      // debug override
+  const bool fuse1 = li == 1 && net->fuse_first && net->stop_after != 0 && net->tc_cluster == 0 && net->tc_ntile_max == 0;
+  if (fuse1) cs = 1;        // the fused conv1-1 -> conv1-2 kernel runs single CTAs (whole weight tiles per TMA box)
   const size_t pin = kBufs[wr.in].ch, pout = kBufs[wr.out].ch;
   ECSEG_TRY(make_tm_nhwc(ctx, &p.tm_a, net->buf[wr.in], l.cin, in_hw, in_hw, NT, pin, pin * in_hw, pin * in_hw * in_hw, 18, 18, bf16));
   // weight boxes: a whole tap tile, or the half a CTA of a cluster / pair fetches (32-row boxes for the pair's transposed conv)
@@ -592,6 +622,14 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   p.out_choff = wr.choff;
   p.bias = net->b[li]; p.relu = l.relu; p.is_bf16 = bf16;
   p.device_error = &ctx->counters->device_error;
+  p.progress = ctx->counters->progress;
+  if (fuse1) {
+    p.first_src = net->in_tiles ? net->in_tiles : net->in_pre;
+    p.first_from_tiles = net->in_tiles != nullptr;
+    if (grid) p.first_grid = *grid;
+    p.first_w = net->w_first16;
+    p.first_bias = net->b[0];
+  }
   return conv_tc_launch(ctx, p, n_tile, cs, st);
 }
 
@@ -604,8 +642,13 @@ int unet_forward(ecseg_ctx* ctx, const uint8_t* d_tiles, const uint8_t* d_pre, c
   if (d_labels && !grid) { ctx->err = "unet_forward: fused stitch needs the tile grid"; return ECSEG_E_INVALID; }
   const int prec = net->precision;
   if (d_labels) ECSEG_CUDA(cudaMemsetAsync(d_labels, 0, (size_t)grid->h * grid->w, st));  // never-written strips -> 0
+  net->in_tiles = d_tiles; net->in_pre = d_pre;
+  const bool fused_first = prec != ECSEG_PREC_FP32 && net->fuse_first && net->stop_after != 0 && net->tc_cluster == 0 &&
+                           net->tc_ntile_max == 0;
   for (int li = 0; li < 23; ++li) {
-    if (li == 0) {
+    if (li == 0 && fused_first) {
+      continue;     // conv1-1 is computed inside conv1-2's halo producer (conv_tc.cu, FUSE1)
+    } else if (li == 0) {
       if (prec == ECSEG_PREC_FP32) ECSEG_TRY(run_first<float>(ctx, d_tiles, d_pre, grid, n, st));
       else if (prec == ECSEG_PREC_BF16) ECSEG_TRY(run_first<__nv_bfloat16>(ctx, d_tiles, d_pre, grid, n, st));
       else ECSEG_TRY(run_first<__half>(ctx, d_tiles, d_pre, grid, n, st));

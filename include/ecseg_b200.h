@@ -209,6 +209,10 @@ int ecseg_debug_layer_output(ecseg_ctx* ctx, int layer, int n, float* d_out, voi
  * Any other value (e.g. -1) leaves that setting unchanged. */
 int ecseg_debug_set(ecseg_ctx* ctx, int stop_after_layer, int tc_cluster, int tc_ntile_max);
 
+/* Progress markers the tcgen05 kernels' roles of CTA 0 leave behind (producer, MMA, epilogue, conv1-1 generator, ...):
+ * read on a side stream, so it answers while a kernel of the context is still running (pipeline bring-up / hangs). */
+int ecseg_debug_progress(ecseg_ctx* ctx, int32_t out[8]);
+
 /* Synchronise and read the device-side pipeline watchdog flag (0 = healthy). */
 int ecseg_device_error(ecseg_ctx* ctx, int* code);
 
