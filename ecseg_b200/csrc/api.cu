@@ -76,6 +76,7 @@ void ecseg_ctx_destroy(ecseg_ctx* ctx) {
   cudaDeviceSynchronize();
   unet_destroy(ctx);
   art_free_workspace(ctx);
+  if (ctx->trace) cudaFree(ctx->trace);
   void* ptrs[] = {ctx->L, ctx->area, ctx->sum_y, ctx->sum_x, ctx->flag, ctx->tmp_a, ctx->tmp_b, ctx->chrom_cy,
                   ctx->chrom_cx, ctx->nuc_roots, ctx->root_list, ctx->tile_nroots, ctx->counters, ctx->img_in, ctx->pre, ctx->dapi, ctx->labels,
                   ctx->d_n_ec, ctx->d_ec_px};
@@ -407,6 +408,14 @@ int ecseg_debug_progress(ecseg_ctx* ctx, int32_t out[8]) {
   if (!side) ECSEG_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
   ECSEG_CUDA(cudaMemcpyAsync(out, ctx->counters->progress, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, side));
   ECSEG_CUDA(cudaStreamSynchronize(side));
+  return ECSEG_OK;
+}
+
+int ecseg_debug_trace(ecseg_ctx* ctx, int64_t* out, int n) {
+  API_GUARD(ctx);
+  if (!ctx->trace) { ctx->err = "debug_trace: no layer was traced (ECSEG_TRACE_LAYER)"; return ECSEG_E_STATE; }
+  ECSEG_CUDA(cudaDeviceSynchronize());
+  ECSEG_CUDA(cudaMemcpy(out, ctx->trace, (size_t)std::min(n, 4 * 48 * 4) * sizeof(int64_t), cudaMemcpyDeviceToHost));
   return ECSEG_OK;
 }
 

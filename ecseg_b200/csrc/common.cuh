@@ -115,6 +115,7 @@ struct ecseg_ctx {
   size_t png_zcap = 0;
   struct FilesJob { uint8_t* h_png = nullptr; size_t png_cap = 0; int h = 0, w = 0; cudaStream_t st = nullptr; } job;
 
+  long long* trace = nullptr;           // pipeline trace buffer (ecseg_debug_trace), allocated on first use
   ecseg::UNet* net = nullptr;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;

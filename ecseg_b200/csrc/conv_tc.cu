@@ -164,6 +164,10 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
   auto mark = [&](int slot, int v) {
     if (p.progress && blockIdx.x == 0) *reinterpret_cast<volatile int*>(p.progress + slot) = v;
   };
+  // pipeline trace of CTA 0: role r stamps its k-th item at point s
+  auto stamp = [&](int role, int k, int sidx) {
+    if (p.trace && blockIdx.x == 0 && k < kTraceItems) p.trace[(role * kTraceItems + k) * 4 + sidx] = clock64();
+  };
   const int bw = p.W >> 4, bh = p.H >> 4;
   const int n_mblocks = p.n_img * bh * bw;
   const int n_mgroups = (n_mblocks + CS - 1) / CS;
@@ -178,7 +182,9 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
     const bool leader = elect_one();
     int sa = 0, pa = 0, sb = 0, pb = 0;
     bool ok = true;
-    for (int it = cluster_id; it < n_items && ok; it += n_clusters) {
+    int kit = 0;
+    for (int it = cluster_id; it < n_items && ok; it += n_clusters, ++kit) {
+      if (leader) stamp(0, kit, 0);
       const int mg = it % n_mgroups, nch = it / n_mgroups;
       int mb = mg * CS + (int)rank;
       if (mb >= n_mblocks) mb = n_mblocks - 1;    // ghost CTA of an odd tail: same loads, no stores
@@ -187,6 +193,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
       for (int ch = 0; ch < p.cin_chunks && ok; ++ch) {
         if (!FUSE1) ok = __all_sync(0xffffffffu, mbar_wait(empty_a(sa), pa ^ 1, p.device_error, 1));
         if (!ok) break;
+        if (leader && ch == 0) stamp(0, kit, 1);       // halo stage free
         if (FUSE1) {
           // the halo stage is produced by the generator warps
         } else if (leader) {
@@ -200,7 +207,9 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
         }
         if (++sa == AS) { sa = 0; pa ^= 1; }
         if (NACC == 1) {
-          for (int t = 0; t < 9; ++t) {
+          // resident weights (b_resident: the layer's 9 tap tiles fit the 9 weight stages): loaded once, for the CTA's
+          // first item, and reused by every later item -- the L2 -> SM stream is then the halo alone
+          for (int t = 0; t < 9 && !(p.b_resident && it != cluster_id); ++t) {
             ok = __all_sync(0xffffffffu, mbar_wait(empty_b(sb), pb ^ 1, p.device_error, 2));
             if (!ok) break;
             if (leader) {
@@ -264,6 +273,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
           }
         }
       }
+      if (leader) stamp(0, kit, 2);                      // all loads of the item issued
     }
   } else if (warp == 1 && (!PAIR || rank == 0)) {
     // ===================== MMA issuer (the leader CTA's for a pair) =====================
@@ -284,19 +294,23 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
     };
     int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
     bool ok = true;
-    for (int it = cluster_id; it < n_items && ok; it += n_clusters) {
+    int kit = 0;
+    for (int it = cluster_id; it < n_items && ok; it += n_clusters, ++kit) {
+      if (leader) stamp(1, kit, 0);
       ok = __all_sync(0xffffffffu, mbar_wait(tmem_empty(as), pacc ^ 1, p.device_error, 3));
       if (!ok) break;
+      if (leader) stamp(1, kit, 1);                      // accumulator stage free
       tc_fence_after();
       const uint32_t d0 = tmem_base + (uint32_t)(as * kAccCols);
       for (int ch = 0; ch < p.cin_chunks && ok; ++ch) {
         ok = __all_sync(0xffffffffu, mbar_wait(full_a(sa), pa, p.device_error, 4));
         if (!ok) break;
+        if (leader && ch == 0) stamp(1, kit, 2);         // first halo of the item landed
         const uint32_t a_stage = a_base + sa * kAStride;
         if (NACC == 1) {
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
-            ok = __all_sync(0xffffffffu, mbar_wait(full_b(sb), pb, p.device_error, 5));
+            if (!p.b_resident || it == cluster_id) ok = __all_sync(0xffffffffu, mbar_wait(full_b(sb), pb, p.device_error, 5));
             if (!ok) break;
             tc_fence_after();
             const uint32_t b_lo = sdesc_lo(b_base + sb * kBStage);
@@ -311,7 +325,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
                       idesc, k > 0 ? 1u : first);
               }
               // weight stage reusable (in every CTA of the cluster) once these MMAs retire
-              commit_all(empty_b(sb));
+              if (!p.b_resident) commit_all(empty_b(sb));
             }
             __syncwarp();
             if (++sb == BS) { sb = 0; pb ^= 1; }
@@ -357,6 +371,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
       }
       if (leader) commit_all(tmem_full(as), /*local_only=*/true);     // accumulators complete -> epilogue
       if (leader) mark(1, it + 1);
+      if (leader) stamp(1, kit, 3);                      // every MMA of the item issued
       __syncwarp();
       if (++as == kAccStages) { as = 0; pacc ^= 1; }
     }
@@ -504,7 +519,9 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
     const int bar_a = 1 + eg, bar_b = 3 + eg;
     int as = 0, pacc = 0;
     bool ok = true;
-    for (int it = cluster_id; it < n_items && ok; it += n_clusters) {
+    int kit = 0;
+    for (int it = cluster_id; it < n_items && ok; it += n_clusters, ++kit) {
+      if (e0) stamp(2 + eg, kit, 0);
       const int mg = it % n_mgroups, nch = it / n_mgroups;
       const int mb_raw = mg * CS + (int)rank;
       const bool ghost = mb_raw >= n_mblocks;
@@ -513,6 +530,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
       const int y0 = (rem / bw) << 4, x0 = (rem % bw) << 4;
       ok = mbar_wait<64>(tmem_full(as), pacc, p.device_error, 6);
       if (!ok) break;
+      if (e0) stamp(2 + eg, kit, 1);                     // accumulators complete
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccCols);
       int unit = 0;
@@ -586,9 +604,11 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
         }
       }
       tc_fence_before();
+      if (e0) stamp(2 + eg, kit, 2);                     // this group's units stored
       if (e0 && eg == 0) mark(2, it + 1);
       if (PAIR) mbar_arrive_cluster(tmem_empty(as), 0);   // the leader's MMA warp waits for both CTAs' epilogues
       else mbar_arrive(tmem_empty(as));
+      if (e0) stamp(2 + eg, kit, 3);                     // accumulator stage handed back
       if (++as == kAccStages) { as = 0; pacc ^= 1; }
     }
     if (e0) bulk_wait<0>();
@@ -611,7 +631,9 @@ int launch_cfg(ecseg_ctx* ctx, ConvTcParams& p, cudaStream_t st) {
   const int budget = 227 * 1024;
   p.a_stages = (N_TILE == 64 && NACC == 1 && !FUSE1) ? 3 : 2;
   p.b_stages = (budget - smem_bytes(N_TILE, NACC, PAIR, p.a_stages, 0, FUSE1)) / b_stage_bytes(N_TILE, NACC, PAIR);
-  if (p.b_stages > 8) p.b_stages = 8;
+  if (p.b_resident && (NACC != 1 || FUSE1 || p.cin_chunks != 1 || p.n_chunks != 1 || p.b_stages < 9)) p.b_resident = 0;
+  if (p.b_resident) p.b_stages = 9;      // one stage per tap, filled once
+  else if (p.b_stages > 8) p.b_stages = 8;
   if (p.b_stages < 2 || 2 * p.a_stages + 2 * p.b_stages + 5 > kMaxBars) { ctx->err = "conv_tc: bad pipeline configuration"; return ECSEG_E_INVALID; }
   const int smem = smem_bytes(N_TILE, NACC, PAIR, p.a_stages, p.b_stages, FUSE1);
   static bool attr_done = false;

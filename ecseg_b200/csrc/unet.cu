@@ -623,6 +623,14 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   p.bias = net->b[li]; p.relu = l.relu; p.is_bf16 = bf16;
   p.device_error = &ctx->counters->device_error;
   p.progress = ctx->counters->progress;
+  if (const char* e = getenv("ECSEG_TRACE_LAYER")) {       // pipeline trace of one layer (tools/trace_layer.py)
+    if (atoi(e) == li) {
+      if (!ctx->trace) ECSEG_CUDA(cudaMalloc((void**)&ctx->trace, 4 * kTraceItems * 4 * sizeof(long long)));
+      ECSEG_CUDA(cudaMemsetAsync(ctx->trace, 0, 4 * kTraceItems * 4 * sizeof(long long), st));
+      p.trace = ctx->trace;
+    }
+  }
+  p.b_resident = (!l.convT && l.cin == 64 && rows == n_tile && !getenv("ECSEG_NO_RESIDENT_B")) ? 1 : 0;   // conv1-2 (unfused), conv1-4
   if (fuse1) {
     p.first_src = net->in_tiles ? net->in_tiles : net->in_pre;
     p.first_from_tiles = net->in_tiles != nullptr;
