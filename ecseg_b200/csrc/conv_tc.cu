@@ -38,9 +38,15 @@ using namespace tc;
 
 constexpr int kThreads = 384;          // warps 0-3: producer / MMA / TMEM alloc / spare, warps 4-11: two epilogue groups
 constexpr int kEpiWarp0 = 4;
-constexpr int kHaloPitch = 18;
-constexpr int kABytes = 18 * 18 * 128;             // bytes one halo load delivers
-constexpr int kAStride = 41 * 1024;                // stage footprint (1024-aligned for SWIZZLE_128B)
+// M block of an item: 16 rows x kBlkW columns.  A convolution works on 16x16 blocks (two M=128 halves sharing every
+// weight stage).  A transposed convolution keeps four accumulators (one per output parity), so a 16x16 block would
+// fill all 512 TMEM columns and the epilogue could never overlap the next item's MMAs (measured with the pipeline
+// trace: MMA 6.6k + epilogue 7.5k cycles strictly alternating); it works on 16x8 blocks instead (256 columns, double
+// buffered) at the price of a slightly larger halo-to-block ratio.
+__host__ __device__ constexpr int blk_w(int nacc) { return nacc == 4 ? 8 : 16; }
+__host__ __device__ constexpr int halo_pitch(int nacc) { return blk_w(nacc) + 2; }
+__host__ __device__ constexpr int a_bytes(int nacc) { return 18 * halo_pitch(nacc) * 128; }             // one halo load
+__host__ __device__ constexpr int a_stride(int nacc) { return (a_bytes(nacc) + 1023) / 1024 * 1024; }   // stage footprint
 constexpr int kOutStage = 128 * 128;               // staging tile: 128 pixels x 64 channels x 2 B
 constexpr int kPoolStage = 32 * 128;               // pooled staging tile: 32 pixels x 64 channels
 constexpr int kMaxBars = 32;
@@ -81,7 +87,7 @@ __host__ __device__ constexpr int b_stage_bytes(int n_tile, int nacc, bool pair)
   return (nacc == 4 ? 4 * n_tile * 128 : n_tile * 128) / (pair ? 2 : 1);
 }
 __host__ __device__ constexpr int smem_bytes(int n_tile, int nacc, bool pair, int a_stages, int b_stages, bool fuse1 = false) {
-  return a_stages * kAStride + b_stages * b_stage_bytes(n_tile, nacc, pair) + (fuse1 ? kGenBytes : 0) + 2 * kOutStage +
+  return a_stages * a_stride(nacc) + b_stages * b_stage_bytes(n_tile, nacc, pair) + (fuse1 ? kGenBytes : 0) + 2 * kOutStage +
          2 * kPoolStage + kMaxCout * 4 + kMaxBars * 8 + 16 + 1024;
 }
 
@@ -90,7 +96,9 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
   static_assert(!FUSE1 || (N_TILE == 64 && NACC == 1 && CS == 1 && !PAIR), "conv1-1 fusion is built for the conv1-2 configuration");
   constexpr int kBBytes = N_TILE * 128;                 // one tap's weight tile
   constexpr int kBStage = b_stage_bytes(N_TILE, NACC, PAIR);  // conv: one tap; transposed conv: one view (up to 4 taps)
-  constexpr int kAccCols = 2 * NACC * N_TILE;
+  constexpr int kHaloPitch = halo_pitch(NACC), kABytes = a_bytes(NACC), kAStride = a_stride(NACC);
+  constexpr int kBlkW = blk_w(NACC), kHalves = kBlkW / 8;
+  constexpr int kAccCols = kHalves * NACC * N_TILE;
   constexpr int kAccStages = (2 * kAccCols <= 512) ? 2 : 1;
   constexpr int kTmemCols = 512;
   static_assert(kAccCols <= 512, "accumulators exceed TMEM");
@@ -168,7 +176,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
   auto stamp = [&](int role, int k, int sidx) {
     if (p.trace && blockIdx.x == 0 && k < kTraceItems) p.trace[(role * kTraceItems + k) * 4 + sidx] = clock64();
   };
-  const int bw = p.W >> 4, bh = p.H >> 4;
+  const int bw = p.W / kBlkW, bh = p.H >> 4;
   const int n_mblocks = p.n_img * bh * bw;
   const int n_mgroups = (n_mblocks + CS - 1) / CS;
   const int n_items = n_mgroups * p.n_chunks;
@@ -189,7 +197,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
       int mb = mg * CS + (int)rank;
       if (mb >= n_mblocks) mb = n_mblocks - 1;    // ghost CTA of an odd tail: same loads, no stores
       const int img = mb / (bh * bw), rem = mb % (bh * bw);
-      const int y0 = (rem / bw) << 4, x0 = (rem % bw) << 4;
+      const int y0 = (rem / bw) << 4, x0 = (rem % bw) * kBlkW;
       for (int ch = 0; ch < p.cin_chunks && ok; ++ch) {
         if (!FUSE1) ok = __all_sync(0xffffffffu, mbar_wait(empty_a(sa), pa ^ 1, p.device_error, 1));
         if (!ok) break;
@@ -320,7 +328,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                for (int half = 0; half < 2; ++half)
+                for (int half = 0; half < kHalves; ++half)
                   mma(d0 + half * N_TILE, sdesc_join(a_lo + half * 64 + k * 2, a_hi), sdesc_join(b_lo + k * 2, b_hi),
                       idesc, k > 0 ? 1u : first);
               }
@@ -344,7 +352,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
+                for (int half = 0; half < kHalves; ++half) {
                   const uint32_t d = d0 + half * (4 * N_TILE);
                   const uint64_t ad = sdesc_join(a_lo + half * 64 + k * 2, a_hi);
                   if (v == 0) {
@@ -388,7 +396,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
       if (mb >= n_mblocks) mb = n_mblocks - 1;
       img = mb / (bh * bw);
       const int rem = mb % (bh * bw);
-      y0 = (rem / bw) << 4; x0 = (rem % bw) << 4;
+      y0 = (rem / bw) << 4; x0 = (rem % bw) * kBlkW;
     };
     // input byte e of the 20x20 patch around block (y0, x0) of tile `img`; zero outside the tile ('same' padding of conv1-1)
     auto patch_byte = [&](int img, int y0, int x0, int e) -> uint8_t {
@@ -527,7 +535,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
       const bool ghost = mb_raw >= n_mblocks;
       const int mb = ghost ? n_mblocks - 1 : mb_raw;
       const int img = mb / (bh * bw), rem = mb % (bh * bw);
-      const int y0 = (rem / bw) << 4, x0 = (rem % bw) << 4;
+      const int y0 = (rem / bw) << 4, x0 = (rem % bw) * kBlkW;
       ok = mbar_wait<64>(tmem_full(as), pacc, p.device_error, 6);
       if (!ok) break;
       if (e0) stamp(2 + eg, kit, 1);                     // accumulators complete
@@ -537,7 +545,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
 #pragma unroll 1
       for (int acc = 0; acc < NACC; ++acc) {
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < kHalves; ++half) {
 #pragma unroll 1
           for (int sl = 0; sl < N_TILE / 64; ++sl) {
             if (((unit++) & 1) != eg) continue;
@@ -629,7 +637,7 @@ int launch_cfg(ecseg_ctx* ctx, ConvTcParams& p, cudaStream_t st) {
   auto kern = k_conv_tc<N_TILE, NACC, CS, PAIR, FUSE1>;
   // pipeline depths: halo stages first (each covers 9 taps of MMA work), the rest goes to weight stages
   const int budget = 227 * 1024;
-  p.a_stages = (N_TILE == 64 && NACC == 1 && !FUSE1) ? 3 : 2;
+  p.a_stages = ((N_TILE == 64 && NACC == 1 && !FUSE1) || NACC == 4) ? 3 : 2;
   p.b_stages = (budget - smem_bytes(N_TILE, NACC, PAIR, p.a_stages, 0, FUSE1)) / b_stage_bytes(N_TILE, NACC, PAIR);
   if (p.b_resident && (NACC != 1 || FUSE1 || p.cin_chunks != 1 || p.n_chunks != 1 || p.b_stages < 9)) p.b_resident = 0;
   if (p.b_resident) p.b_stages = 9;      // one stage per tap, filled once
@@ -641,7 +649,7 @@ int launch_cfg(ecseg_ctx* ctx, ConvTcParams& p, cudaStream_t st) {
     ECSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
     attr_done = true;
   }
-  const int n_mblocks = p.n_img * (p.H >> 4) * (p.W >> 4);
+  const int n_mblocks = p.n_img * (p.H >> 4) * (p.W / blk_w(NACC));
   const int n_items = ((n_mblocks + CS - 1) / CS) * p.n_chunks;
   int clusters = ctx->n_sms / CS;
   if (n_items < clusters) clusters = n_items;

@@ -567,23 +567,24 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   const int out_hw = kTile >> l.level;
   const int in_hw = l.convT ? out_hw / 2 : out_hw;
   const int rows = net->cout_rows[li];
-  // Per-layer kernel variant, measured per layer (profiles/r01_launches_*.txt):
-  //  * CTA pairs (cta_group::2 MMA, "cluster 3") cut the shared-memory operand traffic per MMA (each CTA reads its
-  //    own A rows and only half of B) and win wherever an item has a long K loop;
-  //  * layers whose items are one 64-channel chunk long (conv1-2, conv2-1, up1) lose more to the pair's cross-CTA
-  //    handshakes than they gain and stay on the multicast cluster ("cluster 2");
+  // Per-layer kernel variant, measured per layer (profiles/r01_launches_*.txt, tools/trace_layer.py):
+  //  * CTA pairs (cta_group::2 MMA, "cluster 3") halve the shared-memory B traffic per MMA and run the N = 64 MMAs at
+  //    ~40 instead of ~85 cycles; they win on every layer since the epilogue's remote "accumulators free" arrive
+  //    dropped its cluster-scope release (it cost ~3.3k cycles per item and had made pairs lose on the short layers);
   //  * N tile 128 double-buffers the accumulators in TMEM (epilogue overlapped) and gives finer work items; 256
   //    halves the weight re-fetch and wins only for the 16x16 level.
   int n_tile = l.convT ? 64 : (rows < 128 ? rows : 128);
   int cs = 3;
   if (li == 8 || li == 9) n_tile = 256;             // conv5-1, conv5-2
-  if (li == 1 || li == 2 || li == 19) cs = 2;       // conv1-2, conv2-1, up1
+  if (getenv("ECSEG_TC_TABLE_V1") && (li == 1 || li == 2 || li == 19)) cs = 2;   // the round-1 table, for A/B runs
   if (net->tc_ntile_max > 0 && !l.convT) n_tile = rows < net->tc_ntile_max ? rows : net->tc_ntile_max;   // debug override
   if (net->tc_cluster > 0) cs = net->tc_cluster;                                                      // debug override
   const bool fuse1 = li == 1 && net->fuse_first && net->stop_after != 0 && net->tc_cluster == 0 && net->tc_ntile_max == 0;
   if (fuse1) cs = 1;        // the fused conv1-1 -> conv1-2 kernel runs single CTAs (whole weight tiles per TMA box)
   const size_t pin = kBufs[wr.in].ch, pout = kBufs[wr.out].ch;
-  ECSEG_TRY(make_tm_nhwc(ctx, &p.tm_a, net->buf[wr.in], l.cin, in_hw, in_hw, NT, pin, pin * in_hw, pin * in_hw * in_hw, 18, 18, bf16));
+  // halo box: 18 rows x (block width + 2) pixels; transposed convolutions work on 16x8 blocks (conv_tc.cu: blk_w)
+  ECSEG_TRY(make_tm_nhwc(ctx, &p.tm_a, net->buf[wr.in], l.cin, in_hw, in_hw, NT, pin, pin * in_hw, pin * in_hw * in_hw,
+                         l.convT ? 10 : 18, 18, bf16));
   // weight boxes: a whole tap tile, or the half a CTA of a cluster / pair fetches (32-row boxes for the pair's transposed conv)
   const int box_rows = cs == 1 ? n_tile : (cs == 3 && l.convT ? 32 : n_tile / 2);
   ECSEG_TRY(make_tm_wgt(ctx, &p.tm_b, net->w[li], l.cin, 9 * rows, box_rows, bf16));
