@@ -415,7 +415,7 @@ int ecseg_debug_trace(ecseg_ctx* ctx, int64_t* out, int n) {
   API_GUARD(ctx);
   if (!ctx->trace) { ctx->err = "debug_trace: no layer was traced (ECSEG_TRACE_LAYER)"; return ECSEG_E_STATE; }
   ECSEG_CUDA(cudaDeviceSynchronize());
-  ECSEG_CUDA(cudaMemcpy(out, ctx->trace, (size_t)std::min(n, 4 * 48 * 4) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  ECSEG_CUDA(cudaMemcpy(out, ctx->trace, (size_t)std::min(n, kTraceRoles * kTraceItems * 4) * sizeof(int64_t), cudaMemcpyDeviceToHost));
   return ECSEG_OK;
 }
 

@@ -424,6 +424,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
         if (t + kGenThreads * k < 400) const_cast<uint8_t*>(s_patch)[t + kGenThreads * k] = pre[k];
       named_bar_sync(5, kGenThreads);
       if (t == 0) mark(3, it * 8 + 1);
+      if (t == 0) stamp(4, (it - cluster_id) / n_clusters, 0);     // patch in shared memory
       if (it + n_clusters < n_items) {          // prefetch the next item's patch: its latency hides behind this item
         int im2, y2, x2;
         item_origin(it + n_clusters, im2, y2, x2);
@@ -466,6 +467,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
                      idesc1, (uint32_t)k);
         umma_commit(gen_done);
         mark(3, it * 8 + 2);
+        stamp(4, (it - cluster_id) / n_clusters, 1);               // im2col operand built, conv1-1 MMAs issued
       }
       // the halo stage must be free before it is overwritten
       // (a failed wait must take all four warps out together: the named barriers below have no time-out)
@@ -477,6 +479,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
       pg ^= 1;
       tc_fence_after();
       if (t == 0) mark(3, it * 8 + 3);
+      if (t == 0) stamp(4, (it - cluster_id) / n_clusters, 2);     // halo stage free and conv1-1 accumulators complete
       const uint32_t stage = a_base + sa * kAStride;
 #pragma unroll 1
       for (int mt = 0; mt < 3; ++mt) {
@@ -507,7 +510,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
       tc_fence_before();
       fence_async_smem();
       named_bar_sync(5, kGenThreads);
-      if (t == 0) { mbar_arrive(full_a(sa)); mark(3, it * 8 + 4); }
+      if (t == 0) { mbar_arrive(full_a(sa)); mark(3, it * 8 + 4); stamp(4, (it - cluster_id) / n_clusters, 3); }
       if (++sa == AS) { sa = 0; pa ^= 1; }
     }
   } else if (warp >= kEpiWarp0) {

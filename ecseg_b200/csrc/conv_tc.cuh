@@ -8,7 +8,6 @@ namespace ecseg {
 
 constexpr int kMaxPar = 4;   // output-parity classes of a stride-2 transposed conv
 constexpr int kMaxTaps = 9;
-constexpr int kTraceItems = 48;   // items of CTA 0 a pipeline trace covers
 
 // One convolution layer as the kernel sees it.  The GEMM is
 //   D[pixel, cout] = sum over (tap, cin)  A[pixel shifted by tap, cin] * W[tap, cout, cin]
@@ -40,7 +39,7 @@ struct ConvTcParams {
                           // Cin == 64 and Cout == N_TILE; the launcher clears it when they do not fit)
   int* device_error;      // watchdog flag (Counters::device_error)
   int* progress;          // Counters::progress (nullable): role progress markers of CTA 0 for ecseg_debug_progress
-  long long* trace;       // nullable: clock64 stamps of CTA 0, [role 4][item kTraceItems][stamp 4] (ecseg_debug_trace)
+  long long* trace;       // nullable: clock64 stamps of CTA 0, [role kTraceRoles][item kTraceItems][stamp 4] (ecseg_debug_trace)
   // conv1-1 fused in front of this layer (conv1-2 only; first_src == nullptr: off).  The halo stages are then computed
   // in the kernel from the uint8 input (materialised tiles, or the pre-processed image through the tile grid) and
   // tm_a is unused.

@@ -626,8 +626,8 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   p.progress = ctx->counters->progress;
   if (const char* e = getenv("ECSEG_TRACE_LAYER")) {       // pipeline trace of one layer (tools/trace_layer.py)
     if (atoi(e) == li) {
-      if (!ctx->trace) ECSEG_CUDA(cudaMalloc((void**)&ctx->trace, 4 * kTraceItems * 4 * sizeof(long long)));
-      ECSEG_CUDA(cudaMemsetAsync(ctx->trace, 0, 4 * kTraceItems * 4 * sizeof(long long), st));
+      if (!ctx->trace) ECSEG_CUDA(cudaMalloc((void**)&ctx->trace, kTraceRoles * kTraceItems * 4 * sizeof(long long)));
+      ECSEG_CUDA(cudaMemsetAsync(ctx->trace, 0, kTraceRoles * kTraceItems * 4 * sizeof(long long), st));
       p.trace = ctx->trace;
     }
   }

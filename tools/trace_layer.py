@@ -1,33 +1,46 @@
-"""Per-item timeline of one tcgen05 conv layer (CTA 0): ECSEG_TRACE_LAYER=<layer index> python tools/trace_layer.py
-Stamps (clock cycles relative to the first): producer [start, halo stage free, loads issued],
-MMA [start, accumulators free, halo landed, MMAs issued], epilogue g0/g1 [start, accumulators complete, stored]."""
-import ctypes, os, sys
+"""Per-item timeline of tcgen05 conv layers (CTA 0): python tools/trace_layer.py <layer index> [<layer index> ...]
+(or ECSEG_TRACE_LAYER=<layer index>).  Stamps (clock cycles relative to the first): producer [start, halo stage free,
+loads issued], MMA [start, accumulators free, halo landed, MMAs issued], epilogue g0/g1 [start, accumulators complete,
+stored, handed back], conv1-1 generator (fused first layer only) [patch staged, im2col built + MMAs issued, halo stage
+free + conv1-1 accumulators complete, halo stage filled]."""
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from ecseg_b200 import synth, weights as wmod
+from ecseg_b200 import spec, synth, weights as wmod
 from ecseg_b200.engine import Engine
 
+layers = [int(a) for a in sys.argv[1:]] or [int(os.environ.get("ECSEG_TRACE_LAYER", "1"))]
 eng = Engine(0, 2048, 2048)
 eng.load_weights(wmod.make_weights(0), "fp16")
 img = synth.synth_dapi(3, 2048, 2048)
-for _ in range(2):
-    eng.segment_host(img)
-buf = np.zeros(4 * 48 * 4, np.int64)
-eng._chk(eng.lib.ecseg_debug_trace(eng.ctx, buf.ctypes.data, buf.size))
-t = buf.reshape(4, 48, 4).astype(np.float64)
-t0 = t[t > 0].min()
-t = np.where(t > 0, t - t0, np.nan)
-names = ["producer", "mma", "epi0", "epi1"]
-print("layer", os.environ.get("ECSEG_TRACE_LAYER"), "cycles relative to first stamp; items 8..23 of CTA 0")
-for k in range(8, 24):
-    print(f"item {k:2d} | " + " | ".join(f"{names[r]} " + " ".join(f"{t[r, k, s]:8.0f}" for s in range(3 if r == 0 else 4)) for r in range(4)))
-d = np.diff(t[1, 8:40, 3])
-print("mma issue-done period per item: mean %.0f min %.0f max %.0f cycles" % (np.nanmean(d), np.nanmin(d), np.nanmax(d)))
-w_acc = t[1, 8:40, 1] - t[1, 8:40, 0]; w_halo = t[1, 8:40, 2] - t[1, 8:40, 1]; iss = t[1, 8:40, 3] - t[1, 8:40, 2]
-print("mma: wait accumulators %.0f, wait halo %.0f, issue %.0f" % (np.nanmean(w_acc), np.nanmean(w_halo), np.nanmean(iss)))
-for g in (2, 3):
-    w = t[g, 8:40, 1] - t[g, 8:40, 0]; work = t[g, 8:40, 2] - t[g, 8:40, 1]
-    arr = t[g, 8:40, 3] - t[g, 8:40, 2]; gap = t[g, 9:41, 0] - t[g, 8:40, 3]
-    print(f"{names[g]}: wait accumulators %.0f, work %.0f, arrive %.0f, loop gap %.0f" % (np.nanmean(w), np.nanmean(work), np.nanmean(arr), np.nanmean(gap)))
-pw = t[0, 8:40, 1] - t[0, 8:40, 0]; pl = t[0, 8:40, 2] - t[0, 8:40, 1]
-print("producer: wait halo stage %.0f, issue loads (incl. weight-stage waits) %.0f" % (np.nanmean(pw), np.nanmean(pl)))
+R, K = 5, 48
+names = ["producer", "mma", "epi0", "epi1", "gen"]
+for li in layers:
+    os.environ["ECSEG_TRACE_LAYER"] = str(li)      # read by the library at every forward (getenv)
+    for _ in range(2):
+        eng.segment_host(img)
+    buf = np.zeros(R * K * 4, np.int64)
+    eng._chk(eng.lib.ecseg_debug_trace(eng.ctx, buf.ctypes.data, buf.size))
+    t = buf.reshape(R, K, 4).astype(np.float64)
+    t0 = t[t > 0].min()
+    t = np.where(t > 0, t - t0, np.nan)
+    print(f"=== layer {li} ({spec.UNET_LAYERS[li][0]}): cycles relative to the first stamp; items 8..19 of CTA 0")
+    roles = [r for r in range(R) if not np.all(np.isnan(t[r]))]
+    for k in range(8, 20):
+        print(f"item {k:2d} | " + " | ".join(f"{names[r]} " + " ".join(f"{t[r, k, s]:7.0f}" for s in range(3 if r == 0 else 4)) for r in roles))
+    with np.errstate(all="ignore"):
+        d = np.diff(t[1, 8:40, 3])
+        print("mma issue-done period per item: mean %.0f min %.0f max %.0f cycles" % (np.nanmean(d), np.nanmin(d), np.nanmax(d)))
+        w_acc = t[1, 8:40, 1] - t[1, 8:40, 0]; w_halo = t[1, 8:40, 2] - t[1, 8:40, 1]; iss = t[1, 8:40, 3] - t[1, 8:40, 2]
+        print("mma: wait accumulators %.0f, wait halo %.0f, issue %.0f" % (np.nanmean(w_acc), np.nanmean(w_halo), np.nanmean(iss)))
+        for g in (2, 3):
+            w = t[g, 8:40, 1] - t[g, 8:40, 0]; work = t[g, 8:40, 2] - t[g, 8:40, 1]
+            arr = t[g, 8:40, 3] - t[g, 8:40, 2]; gap = t[g, 9:41, 0] - t[g, 8:40, 3]
+            print(f"{names[g]}: wait accumulators %.0f, work %.0f, arrive %.0f, loop gap %.0f" % (np.nanmean(w), np.nanmean(work), np.nanmean(arr), np.nanmean(gap)))
+        pw = t[0, 8:40, 1] - t[0, 8:40, 0]; pl = t[0, 8:40, 2] - t[0, 8:40, 1]
+        print("producer: wait halo stage %.0f, issue loads (incl. weight-stage waits) %.0f" % (np.nanmean(pw), np.nanmean(pl)))
+        if 4 in roles:
+            g = t[4, 8:40]
+            print("gen: im2col+issue %.0f, wait (stage free & conv1-1 done) %.0f, readback+store %.0f, next patch %.0f" % (
+                np.nanmean(g[:, 1] - g[:, 0]), np.nanmean(g[:, 2] - g[:, 1]), np.nanmean(g[:, 3] - g[:, 2]),
+                np.nanmean(t[4, 9:41, 0] - g[:, 3])))
