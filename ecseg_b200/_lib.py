@@ -10,7 +10,8 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libecseg_b200.so")
+# ECSEG_B200_LIB: another build of the same library (A/B runs of two kernel versions on one GPU box)
+LIB_PATH = os.environ.get("ECSEG_B200_LIB") or os.path.join(_HERE, "libecseg_b200.so")
 
 # name -> (restype, argtypes).  Every symbol declared in include/ecseg_b200.h is listed here and
 # tests/test_abi.py checks the two stay in sync.

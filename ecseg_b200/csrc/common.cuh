@@ -12,7 +12,7 @@
 namespace ecseg {
 
 constexpr int kTraceItems = 48;   // items of CTA 0 a pipeline trace covers (ecseg_debug_trace)
-constexpr int kTraceRoles = 5;    // producer, MMA issuer, epilogue group 0 / 1, conv1-1 generator
+constexpr int kTraceRoles = 6;    // producer, MMA issuer, epilogue group 0 / 1, conv1-1 generator, generator detail
 
 constexpr int kTile = 256;      // reference scw            (src/image_tools.py:148)
 constexpr int kOverlap = 25;    // reference overlap_value  (src/image_tools.py:148)

@@ -63,7 +63,8 @@ constexpr int kGenThreads = 128;
 constexpr int kGenWarp0 = 12;
 constexpr int kGenA1Bytes = 384 * 128;           // im2col rows padded to 128 B (SWIZZLE_128B, only k = 0..15 used)
 constexpr int kGenB1Bytes = 64 * 128;
-constexpr int kGenMiscBytes = 1024;              // [0,400) input patch, [512, 768) conv1-1 bias
+constexpr int kGenMiscBytes = 2048;              // [0,800) 20x20 input patch as 16-bit floats, [1024] generator failure flag
+constexpr int kGenFailOff = 1024;
 constexpr int kGenBytes = kGenA1Bytes + kGenB1Bytes + kGenMiscBytes;
 constexpr int kGenTmemCol = 256;                 // behind the two conv1-2 accumulator stages (2 x 128 columns)
 constexpr int kHaloPixels = 18 * 18;
@@ -91,9 +92,9 @@ __host__ __device__ constexpr int smem_bytes(int n_tile, int nacc, bool pair, in
          2 * kPoolStage + kMaxCout * 4 + kMaxBars * 8 + 16 + 1024;
 }
 
-template <int N_TILE, int NACC, int CS, bool PAIR, bool FUSE1>
+template <int N_TILE, int NACC, int CS, bool PAIR, bool FUSE1, bool BF16>
 __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) k_conv_tc(const __grid_constant__ ConvTcParams p) {
-  static_assert(!FUSE1 || (N_TILE == 64 && NACC == 1 && CS == 1 && !PAIR), "conv1-1 fusion is built for the conv1-2 configuration");
+  static_assert(!FUSE1 || (N_TILE == 64 && NACC == 1 && (CS == 1 || PAIR)), "conv1-1 fusion is built for the conv1-2 configuration");
   constexpr int kBBytes = N_TILE * 128;                 // one tap's weight tile
   constexpr int kBStage = b_stage_bytes(N_TILE, NACC, PAIR);  // conv: one tap; transposed conv: one view (up to 4 taps)
   constexpr int kHaloPitch = halo_pitch(NACC), kABytes = a_bytes(NACC), kAStride = a_stride(NACC);
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
   auto tmem_full = [&](int s) { return bar_base + 8u * (2 * AS + 2 * BS + s); };
   auto tmem_empty = [&](int s) { return bar_base + 8u * (2 * AS + 2 * BS + 2 + s); };
   const uint32_t gen_done = bar_base + 8u * (2 * AS + 2 * BS + 4);
+  const uint32_t a1_full = bar_base + 8u * (2 * AS + 2 * BS + 5);   // FUSE1 pair: both CTAs' im2col operands built (leader's barrier)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + AS * kAStride + BS * kBStage + kGen + 2 * kOutStage +
                                                         2 * kPoolStage + kMaxCout * 4 + kMaxBars * 8);
 
@@ -134,10 +136,11 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
   const int cluster_id = blockIdx.x / CS, n_clusters = gridDim.x / CS;
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < AS; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
+    // a generated halo stage of a pair is complete when both CTAs' generators have arrived on the leader's barrier
+    for (int s = 0; s < AS; ++s) { mbar_init(full_a(s), (FUSE1 && PAIR) ? 2 : 1); mbar_init(empty_a(s), 1); }
     for (int s = 0; s < BS; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), PAIR ? 1 : CS); }
     for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), PAIR ? 512 : 256); }
-    if (FUSE1) mbar_init(gen_done, 1);
+    if (FUSE1) { mbar_init(gen_done, 1); mbar_init(a1_full, 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
     if (PAIR) tmem_alloc_2sm(smem_u32(tmem_ptr_smem), kTmemCols);
@@ -152,15 +155,17 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
     for (int i = threadIdx.x; i < cout; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
   }
   if (FUSE1 && warp >= kGenWarp0) {
-    // conv1-1 weights [64 cout][32 k] 16-bit -> K-major SWIZZLE_128B rows (four 16-byte chunks per row); fp32 bias
+    // conv1-1 weights [64 cout][32 k] 16-bit -> K-major SWIZZLE_128B rows (four 16-byte chunks per row); fp32 bias.
+    // A CTA of a pair keeps its half of the output channels (B rows) in shared-memory rows 0..31.
     const int t = threadIdx.x - kGenWarp0 * 32;
+    constexpr int kB1Rows = PAIR ? 32 : 64;
 #pragma unroll
-    for (int e = t; e < 64 * 4; e += kGenThreads) {
+    for (int e = t; e < kB1Rows * 4; e += kGenThreads) {
       const int row = e >> 2, j = e & 3;
-      const uint4 v = reinterpret_cast<const uint4*>(p.first_w)[row * 4 + j];
+      const uint4 v = reinterpret_cast<const uint4*>(p.first_w)[((PAIR ? (int)rank * 32 : 0) + row) * 4 + j];
       st_shared_v4(g_b1 + (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4), v);
     }
-    if (t == 0) *reinterpret_cast<volatile int*>(smem + (g_misc - a_base) + 768) = 0;     // generator failure flag
+    if (t == 0) *reinterpret_cast<volatile int*>(smem + (g_misc - a_base) + kGenFailOff) = 0;     // generator failure flag
     fence_async_smem();
   }
   tc_fence_before();
@@ -287,7 +292,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
     // ===================== MMA issuer (the leader CTA's for a pair) =====================
     const bool leader = elect_one();
     constexpr int kM = PAIR ? 256 : 128;
-    const uint32_t idesc = make_idesc(kM, N_TILE, p.is_bf16);
+    const uint32_t idesc = make_idesc(kM, N_TILE, BF16);
     const uint32_t a_hi = sdesc_hi(kHaloPitch * 128), b_hi = sdesc_hi(1024);
     auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t accumulate) {
       if (PAIR) umma_f16_2sm(d, ad, bd, id, accumulate);
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
           }
         } else {
           // transposed conv: TMEM columns [half][acc'][N_TILE]; one weight stage per halo view
-          const uint32_t idesc4 = make_idesc(kM, 4 * N_TILE, p.is_bf16), idesc2 = make_idesc(kM, 2 * N_TILE, p.is_bf16);
+          const uint32_t idesc4 = make_idesc(kM, 4 * N_TILE, BF16), idesc2 = make_idesc(kM, 2 * N_TILE, BF16);
 #pragma unroll
           for (int v = 0; v < kNumViews; ++v) {
             ok = __all_sync(0xffffffffu, mbar_wait(full_b(sb), pb, p.device_error, 5));
@@ -385,67 +390,69 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
     }
   } else if (FUSE1 && warp >= kGenWarp0) {
     // ===================== conv1-1 generator (FUSE1) =====================
+    // Software pipeline over the CTA's items: while the halo of item i is read back from TMEM (conv1-1 accumulators
+    // -> ReLU -> 16-bit rows of the halo stage), the im2col operand of item i+1 is already built, and its MMAs are
+    // issued the moment the read-back has drained the accumulators -- ahead of conv1-2's MMAs for item i in the
+    // tensor pipe's queue.  Per item the chain is  build(i+1) -> read-back(i) -> issue(i+1) -> stage i full.
+    static_assert(kTile == 256, "item origin below uses the 16 x 16 blocks of a 256 x 256 tile");
     const int t = threadIdx.x - kGenWarp0 * 32;           // 0..127 = TMEM lane = row of an M=128 tile
     const int q = warp & 3;
-    const uint8_t* s_patch = smem + (g_misc - a_base);
-    const uint32_t idesc1 = make_idesc(128, 64, p.is_bf16);
+    const uint32_t s_patch = g_misc;                      // 20x20 input patch, 16-bit floats (0..255 is exact in both types)
+    uint16_t* s_patch_w = reinterpret_cast<uint16_t*>(smem + (g_misc - a_base));
+    const uint32_t one16 = BF16 ? 0x3F80u : 0x3C00u;
+    const uint32_t idesc1 = make_idesc(PAIR ? 256 : 128, 64, BF16);
     const uint32_t hi1 = sdesc_hi(1024);
     const uint32_t t1 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)kGenTmemCol;
+    // block origin of item `it` (n_chunks == 1: item = M group); no integer divisions on this path
     auto item_origin = [&](int it, int& img, int& y0, int& x0) {
-      int mb = it % n_mgroups;
+      int mb = it * CS + (int)rank;
       if (mb >= n_mblocks) mb = n_mblocks - 1;
-      img = mb / (bh * bw);
-      const int rem = mb % (bh * bw);
-      y0 = (rem / bw) << 4; x0 = (rem % bw) * kBlkW;
+      img = mb >> 8; y0 = ((mb >> 4) & 15) << 4; x0 = (mb & 15) << 4;
     };
-    // input byte e of the 20x20 patch around block (y0, x0) of tile `img`; zero outside the tile ('same' padding of conv1-1)
-    auto patch_byte = [&](int img, int y0, int x0, int e) -> uint8_t {
-      const int yy = y0 - 2 + e / 20, xx = x0 - 2 + e % 20;
-      if (e >= 400 || yy < 0 || yy >= kTile || xx < 0 || xx >= kTile) return 0;
-      if (p.first_from_tiles) return p.first_src[((size_t)img * kTile + yy) * kTile + xx];
-      const int ri = img % p.first_grid.nr, ci = img / p.first_grid.nr;
-      return p.first_src[(size_t)(p.first_grid.start_r(ri) + yy) * p.first_grid.w + p.first_grid.start_c(ci) + xx];
-    };
-    uint8_t pre[4] = {0, 0, 0, 0};
-    if (cluster_id < n_items) {
-      int img, y0, x0;
-      item_origin(cluster_id, img, y0, x0);
+    // this thread's (up to 4) bytes of the 20x20 patch around block (y0, x0) of tile `img`; zero outside the tile
+    // ('same' padding of conv1-1)
+    int pdy[4], pdx[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) pre[k] = patch_byte(img, y0, x0, t + kGenThreads * k);
-    }
-    int sa = 0, pa = 0, pg = 0;
-    bool ok = true;
-    for (int it = cluster_id; it < n_items && ok; it += n_clusters) {
+    for (int k = 0; k < 4; ++k) { const int e = t + kGenThreads * k; pdy[k] = e / 20 - 2; pdx[k] = e % 20 - 2; }
+    auto load_patch = [&](int it, uint8_t pre[4]) {
       int img, y0, x0;
       item_origin(it, img, y0, x0);
-      // the previous item's patch / im2col readers are done (its MMAs completed before gen_done fired)
+      const uint8_t* src;
+      int pitch;
+      if (p.first_from_tiles) { src = p.first_src + (size_t)img * kTile * kTile; pitch = kTile; }
+      else {
+        const int ci = img / p.first_grid.nr, ri = img - ci * p.first_grid.nr;
+        src = p.first_src + (size_t)p.first_grid.start_r(ri) * p.first_grid.w + p.first_grid.start_c(ci);
+        pitch = p.first_grid.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int yy = y0 + pdy[k], xx = x0 + pdx[k];
+        const bool in = t + kGenThreads * k < 400 && yy >= 0 && yy < kTile && xx >= 0 && xx < kTile;
+        pre[k] = in ? src[(size_t)yy * pitch + xx] : (uint8_t)0;
+      }
+    };
+    // stage the patch, then the im2col rows: halo pixel pix = mt*128 + t -> taps (ky, kx) at patch[(hy + ky) * 20 + hx + kx]
+    auto build_a1 = [&](const uint8_t pre[4]) {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (t + kGenThreads * k < 400) const_cast<uint8_t*>(s_patch)[t + kGenThreads * k] = pre[k];
+        if (t + kGenThreads * k < 400) s_patch_w[t + kGenThreads * k] = (uint16_t)(pack2((float)pre[k], 0.f, BF16) & 0xffffu);
       named_bar_sync(5, kGenThreads);
-      if (t == 0) mark(3, it * 8 + 1);
-      if (t == 0) stamp(4, (it - cluster_id) / n_clusters, 0);     // patch in shared memory
-      if (it + n_clusters < n_items) {          // prefetch the next item's patch: its latency hides behind this item
-        int im2, y2, x2;
-        item_origin(it + n_clusters, im2, y2, x2);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) pre[k] = patch_byte(im2, y2, x2, t + kGenThreads * k);
-      }
-      // im2col rows: halo pixel pix = mt*128 + t -> taps (ky, kx) at patch[(hy + ky) * 20 + hx + kx]
 #pragma unroll
       for (int mt = 0; mt < 3; ++mt) {
         const int pix = mt * 128 + t;
         if (pix < kHaloPixels) {
           const int hy = pix / 18, hx = pix % 18;
-          float v[9];
+          uint32_t v[9];
+          const uint32_t pb = s_patch + (uint32_t)((hy * 20 + hx) * 2);
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) v[ky * 3 + kx] = (float)s_patch[(hy + ky) * 20 + hx + kx];
+            for (int kx = 0; kx < 3; ++kx) v[ky * 3 + kx] = ld_shared_u16(pb + (uint32_t)((ky * 20 + kx) * 2));
           uint4 c0, c1;
-          c0.x = pack2(v[0], v[1], p.is_bf16); c0.y = pack2(v[2], v[3], p.is_bf16);
-          c0.z = pack2(v[4], v[5], p.is_bf16); c0.w = pack2(v[6], v[7], p.is_bf16);
-          c1.x = pack2(v[8], 1.f, p.is_bf16); c1.y = 0u; c1.z = 0u; c1.w = 0u;     // k = 9: ones column, meets the bias row
+          c0.x = v[0] | (v[1] << 16); c0.y = v[2] | (v[3] << 16);
+          c0.z = v[4] | (v[5] << 16); c0.w = v[6] | (v[7] << 16);
+          c1.x = v[8] | (one16 << 16); c1.y = 0u; c1.z = 0u; c1.w = 0u;     // k = 9: ones column, meets the bias row
           // k = 0..15 meets the high halves of the weights, k = 16..31 the same taps again for the low halves
           const uint32_t rowa = g_a1 + (uint32_t)pix * 128u;
           st_shared_v4(rowa + (uint32_t)((0 ^ (pix & 7)) << 4), c0);
@@ -455,31 +462,66 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
         }
       }
       fence_async_smem();
-      named_bar_sync(5, kGenThreads);
-      if (t == 0) {
+    };
+    // conv1-1 MMAs of the item whose operand was just built (thread 0, after a generator barrier).  A pair's MMAs
+    // (M = 256 over both CTAs) are issued by the leader once both CTAs' operands are built.
+    uint32_t pa1 = 0;
+    auto issue_first = [&]() {
+      // Cross-CTA signalling of a pair uses plain remote arrives (a release at cluster scope costs ~900 cycles per
+      // arrive, measured): the operand rows never cross CTAs -- each SM's tensor core reads its own CTA's shared
+      // memory, written and proxy-fenced by that CTA's threads before the generator barrier that precedes this
+      // arrive -- only the go-ahead does.  tests/test_gpu_unet.py compares pair and single-CTA outputs bit for bit.
+      if (PAIR) mbar_arrive_cluster(a1_full, 0);
+      if (!PAIR || rank == 0) {
+        if (PAIR && !mbar_wait(a1_full, pa1, p.device_error, 9)) return;     // (the failure surfaces at the gen_done wait)
         tc_fence_after();
 #pragma unroll
         for (int mt = 0; mt < 3; ++mt)
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_f16(tmem_base + (uint32_t)(kGenTmemCol + mt * 64),
-                     sdesc_join(sdesc_lo(g_a1 + (uint32_t)(mt * 128 * 128)) + k * 2, hi1), sdesc_join(sdesc_lo(g_b1) + k * 2, hi1),
-                     idesc1, (uint32_t)k);
-        umma_commit(gen_done);
-        mark(3, it * 8 + 2);
-        stamp(4, (it - cluster_id) / n_clusters, 1);               // im2col operand built, conv1-1 MMAs issued
+          for (int k = 0; k < 2; ++k) {
+            const uint32_t d1 = tmem_base + (uint32_t)(kGenTmemCol + mt * 64);
+            const uint64_t ad1 = sdesc_join(sdesc_lo(g_a1 + (uint32_t)(mt * 128 * 128)) + k * 2, hi1);
+            const uint64_t bd1 = sdesc_join(sdesc_lo(g_b1) + k * 2, hi1);
+            if (PAIR) umma_f16_2sm(d1, ad1, bd1, idesc1, (uint32_t)k);
+            else umma_f16(d1, ad1, bd1, idesc1, (uint32_t)k);
+          }
+        if (PAIR) umma_commit_2sm(gen_done, (uint16_t)3);
+        else umma_commit(gen_done);
       }
-      // the halo stage must be free before it is overwritten
-      // (a failed wait must take all four warps out together: the named barriers below have no time-out)
-      volatile int* s_fail = reinterpret_cast<volatile int*>(smem + (g_misc - a_base) + 768);
-      if (!(mbar_wait<64>(empty_a(sa), pa ^ 1, p.device_error, 7) && mbar_wait<64>(gen_done, pg, p.device_error, 8))) *s_fail = 1;
+    };
+    volatile int* s_fail = reinterpret_cast<volatile int*>(smem + (g_misc - a_base) + kGenFailOff);
+    uint8_t pre[4] = {0, 0, 0, 0};
+    int sa = 0, pa = 0, pg = 0;
+    bool ok = true;
+    if (cluster_id < n_items) {        // prologue: operand and MMAs of the first item, patch of the second in registers
+      load_patch(cluster_id, pre);
+      build_a1(pre);
+      if (cluster_id + n_clusters < n_items) load_patch(cluster_id + n_clusters, pre);
       named_bar_sync(5, kGenThreads);
-      ok = *s_fail == 0;
-      if (!ok) break;
+      if (t == 0) issue_first();
+      pa1 ^= 1;
+    }
+    int kit = 0;
+    for (int it = cluster_id; it < n_items && ok; it += n_clusters, ++kit) {
+      int img, y0, x0;
+      item_origin(it, img, y0, x0);
+      const bool has_next = it + n_clusters < n_items;
+      if (t == 0) { mark(3, it * 8 + 1); stamp(4, kit, 0); }
+      // conv1-1 accumulators of this item complete (=> the im2col operand is free again), halo stage free
+      // (a failed wait must take all four warps out together: the named barriers have no time-out)
+      if (!(mbar_wait<32>(gen_done, pg, p.device_error, 8) && mbar_wait<32>(empty_a(sa), pa ^ 1, p.device_error, 7))) *s_fail = 1;
       pg ^= 1;
       tc_fence_after();
-      if (t == 0) mark(3, it * 8 + 3);
-      if (t == 0) stamp(4, (it - cluster_id) / n_clusters, 2);     // halo stage free and conv1-1 accumulators complete
+      if (t == 0) stamp(4, kit, 1);
+      if (has_next) {
+        build_a1(pre);               // (contains a generator barrier: every thread sees a failure flag set above after it)
+        if (it + 2 * n_clusters < n_items) load_patch(it + 2 * n_clusters, pre);     // latency hides behind the read-back
+      } else {
+        named_bar_sync(5, kGenThreads);
+      }
+      ok = *s_fail == 0;
+      if (!ok) break;
+      if (t == 0) stamp(4, kit, 2);                      // next item's im2col operand built
       const uint32_t stage = a_base + sa * kAStride;
 #pragma unroll 1
       for (int mt = 0; mt < 3; ++mt) {
@@ -488,29 +530,38 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
         const int yy = y0 - 1 + hy, xx = x0 - 1 + hx;
         const bool inside = pix < kHaloPixels && yy >= 0 && yy < kTile && xx >= 0 && xx < kTile;
         const uint32_t rowo = stage + (uint32_t)pix * 128u;
+        uint32_t v[64];
+        tmem_ld32(t1 + (uint32_t)(mt * 64), v);
+        tmem_ld32(t1 + (uint32_t)(mt * 64 + 32), v + 32);
+        tmem_ld_wait();
+        if (t == 0 && mt == 0) stamp(5, kit, 0);         // first M tile's accumulators in registers
+        if (pix < kHaloPixels) {
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          uint32_t v[32];
-          tmem_ld32(t1 + (uint32_t)(mt * 64 + cc * 32), v);
-          tmem_ld_wait();
-          if (pix < kHaloPixels) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              uint4 o;      // bias came through the GEMM; ReLU (models.py:20); pixels outside the tile are conv1-2's zero padding
-              o.x = pack2(fmaxf(__uint_as_float(v[8 * k]), 0.f), fmaxf(__uint_as_float(v[8 * k + 1]), 0.f), p.is_bf16);
-              o.y = pack2(fmaxf(__uint_as_float(v[8 * k + 2]), 0.f), fmaxf(__uint_as_float(v[8 * k + 3]), 0.f), p.is_bf16);
-              o.z = pack2(fmaxf(__uint_as_float(v[8 * k + 4]), 0.f), fmaxf(__uint_as_float(v[8 * k + 5]), 0.f), p.is_bf16);
-              o.w = pack2(fmaxf(__uint_as_float(v[8 * k + 6]), 0.f), fmaxf(__uint_as_float(v[8 * k + 7]), 0.f), p.is_bf16);
-              if (!inside) o = make_uint4(0u, 0u, 0u, 0u);
-              st_shared_v4(rowo + (uint32_t)(((cc * 4 + k) ^ (pix & 7)) << 4), o);
-            }
+          for (int k = 0; k < 8; ++k) {
+            uint4 o;      // bias came through the GEMM; ReLU (models.py:20); pixels outside the tile are conv1-2's zero padding
+            o.x = pack2_relu(__uint_as_float(v[8 * k]), __uint_as_float(v[8 * k + 1]), BF16);
+            o.y = pack2_relu(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3]), BF16);
+            o.z = pack2_relu(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5]), BF16);
+            o.w = pack2_relu(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7]), BF16);
+            if (!inside) o = make_uint4(0u, 0u, 0u, 0u);
+            st_shared_v4(rowo + (uint32_t)((k ^ (pix & 7)) << 4), o);
           }
         }
+        if (t == 0 && mt == 0) stamp(5, kit, 1);
       }
       tc_fence_before();
       fence_async_smem();
-      named_bar_sync(5, kGenThreads);
-      if (t == 0) { mbar_arrive(full_a(sa)); mark(3, it * 8 + 4); stamp(4, (it - cluster_id) / n_clusters, 3); }
+      named_bar_sync(5, kGenThreads);                    // accumulators drained by all, halo stage and next operand written
+      if (t == 0) {
+        stamp(5, kit, 2);
+        if (has_next) issue_first();                     // ahead of conv1-2's MMAs for this item in the tensor pipe
+        stamp(5, kit, 3);
+        if (PAIR) mbar_arrive_cluster(full_a(sa), 0);
+        else mbar_arrive(full_a(sa));
+        mark(3, it * 8 + 4);
+        stamp(4, kit, 3);
+      }
+      pa1 ^= 1;
       if (++sa == AS) { sa = 0; pa ^= 1; }
     }
   } else if (warp >= kEpiWarp0) {
@@ -568,33 +619,30 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
                 f[j] = __uint_as_float(v[j]) + b4.x;         f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
                 f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
               }
+              uint32_t o[16];     // ReLU (models.py:20) rides on the 16-bit conversion
               if (p.relu) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                for (int k = 0; k < 16; ++k) o[k] = pack2_relu(f[2 * k], f[2 * k + 1], BF16);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) o[k] = pack2(f[2 * k], f[2 * k + 1], BF16);
               }
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                uint4 o;
-                o.x = pack2(f[8 * k], f[8 * k + 1], p.is_bf16);     o.y = pack2(f[8 * k + 2], f[8 * k + 3], p.is_bf16);
-                o.z = pack2(f[8 * k + 4], f[8 * k + 5], p.is_bf16); o.w = pack2(f[8 * k + 6], f[8 * k + 7], p.is_bf16);
-                st_shared_v4(so + (uint32_t)(((cc * 4 + k) ^ c) << 4), o);
-              }
+              for (int k = 0; k < 4; ++k)
+                st_shared_v4(so + (uint32_t)(((cc * 4 + k) ^ c) << 4), make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]));
               if (NACC == 1 && p.has_pool) {
                 // fused 2x2/2 max pool (models.py:28,40,52,64): the 2x2 window of pixel (r, c) lives in
-                // lanes ^1 (x neighbour) and ^8 (y neighbour); max commutes with the monotone rounding.
+                // lanes ^1 (x neighbour) and ^8 (y neighbour); max commutes with the monotone rounding, so the
+                // window is reduced on the packed 16-bit pairs (half the shuffles of an fp32 reduction).
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
-                  f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 8));
+                for (int k = 0; k < 16; ++k) {
+                  o[k] = max2(o[k], __shfl_xor_sync(0xffffffffu, o[k], 1), BF16);
+                  o[k] = max2(o[k], __shfl_xor_sync(0xffffffffu, o[k], 8), BF16);
                 }
                 if (pool_lane) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    uint4 o;
-                    o.x = pack2(f[8 * k], f[8 * k + 1], p.is_bf16);     o.y = pack2(f[8 * k + 2], f[8 * k + 3], p.is_bf16);
-                    o.z = pack2(f[8 * k + 4], f[8 * k + 5], p.is_bf16); o.w = pack2(f[8 * k + 6], f[8 * k + 7], p.is_bf16);
-                    st_shared_v4(sq + (uint32_t)(((cc * 4 + k) ^ (pm & 7)) << 4), o);
-                  }
+                  for (int k = 0; k < 4; ++k)
+                    st_shared_v4(sq + (uint32_t)(((cc * 4 + k) ^ (pm & 7)) << 4), make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]));
                 }
               }
             }
@@ -635,17 +683,17 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
   }
 }
 
-template <int N_TILE, int NACC, int CS, bool PAIR, bool FUSE1 = false>
-int launch_cfg(ecseg_ctx* ctx, ConvTcParams& p, cudaStream_t st) {
-  auto kern = k_conv_tc<N_TILE, NACC, CS, PAIR, FUSE1>;
+template <int N_TILE, int NACC, int CS, bool PAIR, bool FUSE1, bool BF16>
+int launch_impl(ecseg_ctx* ctx, ConvTcParams& p, cudaStream_t st) {
+  auto kern = k_conv_tc<N_TILE, NACC, CS, PAIR, FUSE1, BF16>;
   // pipeline depths: halo stages first (each covers 9 taps of MMA work), the rest goes to weight stages
   const int budget = 227 * 1024;
   p.a_stages = ((N_TILE == 64 && NACC == 1 && !FUSE1) || NACC == 4) ? 3 : 2;
   p.b_stages = (budget - smem_bytes(N_TILE, NACC, PAIR, p.a_stages, 0, FUSE1)) / b_stage_bytes(N_TILE, NACC, PAIR);
-  if (p.b_resident && (NACC != 1 || FUSE1 || p.cin_chunks != 1 || p.n_chunks != 1 || p.b_stages < 9)) p.b_resident = 0;
+  if (p.b_resident && (NACC != 1 || (FUSE1 && !PAIR) || p.cin_chunks != 1 || p.n_chunks != 1 || p.b_stages < 9)) p.b_resident = 0;
   if (p.b_resident) p.b_stages = 9;      // one stage per tap, filled once
   else if (p.b_stages > 8) p.b_stages = 8;
-  if (p.b_stages < 2 || 2 * p.a_stages + 2 * p.b_stages + 5 > kMaxBars) { ctx->err = "conv_tc: bad pipeline configuration"; return ECSEG_E_INVALID; }
+  if (p.b_stages < 2 || 2 * p.a_stages + 2 * p.b_stages + 6 > kMaxBars) { ctx->err = "conv_tc: bad pipeline configuration"; return ECSEG_E_INVALID; }
   const int smem = smem_bytes(N_TILE, NACC, PAIR, p.a_stages, p.b_stages, FUSE1);
   static bool attr_done = false;
   if (!attr_done) {
@@ -672,6 +720,13 @@ int launch_cfg(ecseg_ctx* ctx, ConvTcParams& p, cudaStream_t st) {
   return ECSEG_OK;
 }
 
+// the operand type is a template parameter: no predicated fp16 / bf16 twins in the epilogue's pack instructions
+template <int N_TILE, int NACC, int CS, bool PAIR, bool FUSE1 = false>
+int launch_cfg(ecseg_ctx* ctx, ConvTcParams& p, cudaStream_t st) {
+  return p.is_bf16 ? launch_impl<N_TILE, NACC, CS, PAIR, FUSE1, true>(ctx, p, st)
+                   : launch_impl<N_TILE, NACC, CS, PAIR, FUSE1, false>(ctx, p, st);
+}
+
 template <int NACC, int CS, bool PAIR>
 int launch_n(ecseg_ctx* ctx, ConvTcParams& p, int n_tile, cudaStream_t st) {
   switch (n_tile) {
@@ -696,7 +751,7 @@ int conv_tc_launch(ecseg_ctx* ctx, ConvTcParams& p, int n_tile, int cluster, cud
       ctx->err = "conv_tc: the conv1-1 fusion needs the conv1-2 configuration (64 -> 64 channels)";
       return ECSEG_E_INVALID;
     }
-    return launch_cfg<64, 1, 1, false, true>(ctx, p, st);
+    return cluster == 3 ? launch_cfg<64, 1, 2, true, true>(ctx, p, st) : launch_cfg<64, 1, 1, false, true>(ctx, p, st);
   }
   if (p.n_acc == 1) {
     if (cluster == 3) return launch_n<1, 2, true>(ctx, p, n_tile, st);

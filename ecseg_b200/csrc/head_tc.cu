@@ -14,8 +14,12 @@
 //   warp 1 lane 0 : MMA issuer -- 3 M-tiles (384 >= 324 halo rows) x 4 K-steps of
 //                   tcgen05.mma.cta_group::1.kind::f16 M=128 N=48 K=16 into TMEM (double buffered).
 //   warp 2        : TMEM allocation.
-//   warps 4..7    : epilogue -- tcgen05.ld Z rows -> shared memory [324][37] fp32, then each thread
-//                   sums the 9 taps for 2 output pixels, softmax, quantise, argmax, owned write.
+//   warps 4..11   : epilogue -- two groups of four warps (one warp per TMEM lane quarter each) work on alternate
+//                   blocks, each with its own TMEM accumulator stage and its own Z buffer: tcgen05.ld Z rows ->
+//                   shared memory [324][36] fp32 (16-byte stores), then each thread sums the 9 taps for 2 output
+//                   pixels (16-byte loads), softmax, quantise, argmax, owned write.  One group's TMEM drain overlaps
+//                   the other's arithmetic; with a single group the epilogue, not the 839 MB activation read, set
+//                   the pace (362 us against a 131 us HBM floor).
 #include "conv_tc.cuh"
 #include "stitch.cuh"
 #include "tc_common.cuh"
@@ -26,20 +30,24 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
 constexpr int kHalo = 18 * 18;                 // 324 halo pixels
 constexpr int kAStages = 3;
 constexpr int kABytes = kHalo * 128;           // bytes one halo load delivers
-constexpr int kAStride = 3 * 128 * 128;        // 3 M-tiles of 128 rows x 128 B (rows >= 324 are never read back)
+// Stage footprint = the halo rounded up to the swizzle period.  The third M-tile's MMA reads 384 - 324 rows past the
+// halo (into the next stage / the buffers behind the last one): those accumulator rows are never read back.
+constexpr int kAStride = (kABytes + 1023) / 1024 * 1024;
 constexpr int kNRows = 48;                     // 9 taps x 4 classes = 36, padded to a legal UMMA N
 constexpr int kBBytes = kNRows * 128;
 constexpr int kBStride = 6 * 1024;
-constexpr int kZPitch = 37;                    // odd pitch: conflict-free column access
-constexpr int kZBytes = kHalo * kZPitch * 4;
+constexpr int kZPitch = 36;                    // 144-byte rows: 16-byte accesses of 32 consecutive rows take the minimal 4 wavefronts
+constexpr int kZBytes = kHalo * kZPitch * 4;   // one Z buffer per epilogue group
 constexpr int kAccCols = 3 * 64;               // 3 M-tiles, 64-column spacing
 constexpr int kTmemCols = 512;                 // 2 accumulator stages x 192 -> next power of two
 constexpr int kNumBars = 2 * kAStages + 1 + 4;
-constexpr int kSmemBytes = kAStages * kAStride + kBStride + kZBytes + kNumBars * 8 + 16 + 1024;
+constexpr int kSmemBytes = kAStages * kAStride + kBStride + 2 * kZBytes + kNumBars * 8 + 16 + 1024;
+static_assert(kSmemBytes <= 227 * 1024, "head_tc: shared memory");
+static_assert(kAStages * kAStride + 2 * kZBytes >= (kAStages - 1) * kAStride + 3 * 128 * 128, "the last stage's over-read stays inside the allocation");
 
 __global__ void __launch_bounds__(kThreads, 1) k_head_tc(const __grid_constant__ HeadTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -47,13 +55,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_head_tc(const __grid_constant__
   const uint32_t a_base = smem_u32(smem);
   const uint32_t b_base = a_base + kAStages * kAStride;
   float* zs = reinterpret_cast<float*>(smem + kAStages * kAStride + kBStride);
-  const uint32_t bar_base = b_base + kBStride + kZBytes;
+  const uint32_t bar_base = b_base + kBStride + 2 * kZBytes;
   auto full_a = [&](int s) { return bar_base + 8u * s; };
   auto empty_a = [&](int s) { return bar_base + 8u * (kAStages + s); };
   const uint32_t full_b = bar_base + 8u * (2 * kAStages);
   auto tmem_full = [&](int s) { return bar_base + 8u * (2 * kAStages + 1 + s); };
   auto tmem_empty = [&](int s) { return bar_base + 8u * (2 * kAStages + 3 + s); };
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kAStages * kAStride + kBStride + kZBytes + kNumBars * 8);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kAStages * kAStride + kBStride + 2 * kZBytes + kNumBars * 8);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
 
@@ -127,36 +135,39 @@ __global__ void __launch_bounds__(kThreads, 1) k_head_tc(const __grid_constant__
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int q = warp & 3;
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int g = (warp - 4) >> 2;          // epilogue group = accumulator stage = parity of the CTA's block counter
     const int te = q * 32 + lane;           // 0..127
-    int as = 0, pacc = 0;
-    for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+    float* zg = zs + g * (kHalo * kZPitch);
+    uint32_t pacc = 0;
+    int k = 0;
+    for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x, ++k) {
+      if ((k & 1) != g) continue;
       const int img = wk / kBlocksPerImg, rem = wk % kBlocksPerImg;
       const int y0 = (rem / (kTile / 16)) << 4, x0 = (rem % (kTile / 16)) << 4;
-      if (!mbar_wait(tmem_full(as), pacc, p.device_error, 15)) break;
+      if (!mbar_wait<32>(tmem_full(g), pacc, p.device_error, 15)) break;
+      pacc ^= 1;
       tc_fence_after();
-      // Z rows out of TMEM into shared memory (all 128 epilogue threads finished reading the
+      // Z rows out of TMEM into the group's shared-memory buffer (its 128 threads finished reading the
       // previous block's Z: second named barrier below)
 #pragma unroll
       for (int mt = 0; mt < 3; ++mt) {
         const int j = mt * 128 + te;
-        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccCols + mt * 64);
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * kAccCols + mt * 64);
         uint32_t v[32], u[4];
         tmem_ld32(t0, v);
         tmem_ld4(t0 + 32, u);
         tmem_ld_wait();
         if (j < kHalo) {
-          float* zr = zs + j * kZPitch;
+          uint4* zr = reinterpret_cast<uint4*>(zg + j * kZPitch);
 #pragma unroll
-          for (int n = 0; n < 32; ++n) zr[n] = __uint_as_float(v[n]);
-#pragma unroll
-          for (int n = 0; n < 4; ++n) zr[32 + n] = __uint_as_float(u[n]);
+          for (int n = 0; n < 8; ++n) zr[n] = make_uint4(v[4 * n], v[4 * n + 1], v[4 * n + 2], v[4 * n + 3]);
+          zr[8] = make_uint4(u[0], u[1], u[2], u[3]);
         }
       }
       tc_fence_before();
-      mbar_arrive(tmem_empty(as));            // accumulator drained: the next block's MMAs may start
-      if (++as == 2) { as = 0; pacc ^= 1; }
-      named_bar_sync(1, 128);
+      mbar_arrive(tmem_empty(g));             // accumulator drained: the MMAs of this group's next block may start
+      named_bar_sync(1 + g, 128);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int pi = h * 128 + te;
@@ -164,9 +175,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_head_tc(const __grid_constant__
         float z[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-          const float* zr = zs + ((ty + t / 3) * 18 + tx + t % 3) * kZPitch + t * 4;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) z[c] += zr[c];
+          const float4 zt = *reinterpret_cast<const float4*>(zg + ((ty + t / 3) * 18 + tx + t % 3) * kZPitch + t * 4);
+          z[0] += zt.x; z[1] += zt.y; z[2] += zt.z; z[3] += zt.w;
         }
         float pr[4];
         softmax4(z, pr);
@@ -180,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_head_tc(const __grid_constant__
           stitch_write_owned(p.grid, img, y, x, lab, p.labels);
         }
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1 + g, 128);
     }
   }
 

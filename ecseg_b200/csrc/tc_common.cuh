@@ -150,6 +150,25 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int bf16) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// max(x, 0) and the 16-bit rounding in one instruction per pair (cvt.rn.relu): identical to fmaxf + pack2 for finite x
+__device__ __forceinline__ uint32_t pack2_relu(float a, float b, int bf16) {
+  uint32_t d;
+  if (bf16) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  else asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+// element-wise max of two packed 16-bit pairs
+__device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b, int bf16) {
+  uint32_t d;
+  if (bf16) asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  else asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint16_t ld_shared_u16(uint32_t addr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return v;
+}
 
 // 32 lanes x 32 / 4 consecutive columns
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
@@ -272,6 +291,43 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank)
       "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(rank)
       : "memory");
+}
+
+// The same with release semantics at cluster scope: the arriving thread's (and, through a preceding CTA barrier, its
+// CTA's) shared-memory writes are visible to whoever acquires the phase at cluster scope (mbar_wait_cluster).
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(kSuspendHintNs)
+      : "memory");
+  return ok;
+}
+// mbar_wait acquiring at cluster scope (pairs with mbar_arrive_cluster_release from a peer CTA)
+__device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+  if (mbar_try_wait_cluster(bar, parity)) return true;
+  const long long t0 = clock64();
+  unsigned spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 255u) == 0) {
+      if (clock64() - t0 > kWatchdogCycles || *(volatile int*)err_flag != 0) {
+        atomicCAS(err_flag, 0, code);
+        return false;
+      }
+    }
+  }
+  return true;
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

@@ -580,7 +580,9 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   if (net->tc_ntile_max > 0 && !l.convT) n_tile = rows < net->tc_ntile_max ? rows : net->tc_ntile_max;   // debug override
   if (net->tc_cluster > 0) cs = net->tc_cluster;                                                      // debug override
   const bool fuse1 = li == 1 && net->fuse_first && net->stop_after != 0 && net->tc_cluster == 0 && net->tc_ntile_max == 0;
-  if (fuse1) cs = 1;        // the fused conv1-1 -> conv1-2 kernel runs single CTAs (whole weight tiles per TMA box)
+  // the fused conv1-1 -> conv1-2 kernel runs as CTA pairs too (a single CTA's N = 64 MMA takes ~85 cycles: the layer
+  // was MMA-paced at 31 % tensor activity); ECSEG_FUSE1_SINGLE=1 selects the single-CTA variant for A/B runs
+  if (fuse1) cs = getenv("ECSEG_FUSE1_SINGLE") ? 1 : 3;
   const size_t pin = kBufs[wr.in].ch, pout = kBufs[wr.out].ch;
   // halo box: 18 rows x (block width + 2) pixels; transposed convolutions work on 16x8 blocks (conv_tc.cu: blk_w)
   ECSEG_TRY(make_tm_nhwc(ctx, &p.tm_a, net->buf[wr.in], l.cin, in_hw, in_hw, NT, pin, pin * in_hw, pin * in_hw * in_hw,

@@ -96,3 +96,33 @@ def test_batch_larger_than_one_image_and_determinism(setup):
     assert np.array_equal(a, b)
     one = eng.unet_forward(s["tiles"][2:3, ..., 0]).cpu().numpy()
     assert np.array_equal(one[0], a[2])      # tiles are independent: batch composition must not matter
+
+
+def test_fused_first_layer_pair_equals_single_cta(monkeypatch):
+    """The CTA-pair variant of the fused conv1-1 -> conv1-2 kernel hands its generated halo stages to the MMA issuer
+    with plain remote mbarrier arrives (no cluster-scope release); the single-CTA variant has no cross-CTA step and
+    the same arithmetic.  Bit-identical outputs over a whole image's 100 tiles, repeated, is the race check."""
+    from ecseg_b200 import weights as wmod
+    from ecseg_b200.engine import Engine
+    rng = np.random.default_rng(5)
+    tiles = rng.integers(0, 256, (100, 256, 256), dtype=np.uint8)
+    tiles[::7] = 0                      # some all-zero tiles: any stale data would show
+    eng = Engine(0, 2048, 2048)
+    try:
+        eng.load_weights(wmod.make_weights(0), "fp16")
+        dev = eng._dev(tiles, torch.uint8)
+
+        def run():
+            probs = eng.unet_forward(dev)
+            return eng.layer_output(1, 100).clone(), eng.layer_output(2, 100).clone(), probs
+
+        monkeypatch.setenv("ECSEG_FUSE1_SINGLE", "1")
+        ref = run()
+        monkeypatch.delenv("ECSEG_FUSE1_SINGLE")
+        for _ in range(4):
+            got = run()
+            assert eng.device_error() == 0
+            for a, b in zip(got, ref):
+                assert torch.equal(a, b)
+    finally:
+        eng.close()

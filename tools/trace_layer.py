@@ -13,8 +13,8 @@ layers = [int(a) for a in sys.argv[1:]] or [int(os.environ.get("ECSEG_TRACE_LAYE
 eng = Engine(0, 2048, 2048)
 eng.load_weights(wmod.make_weights(0), "fp16")
 img = synth.synth_dapi(3, 2048, 2048)
-R, K = 5, 48
-names = ["producer", "mma", "epi0", "epi1", "gen"]
+R, K = 6, 48
+names = ["producer", "mma", "epi0", "epi1", "gen", "gen+"]
 for li in layers:
     os.environ["ECSEG_TRACE_LAYER"] = str(li)      # read by the library at every forward (getenv)
     for _ in range(2):
@@ -40,7 +40,9 @@ for li in layers:
         pw = t[0, 8:40, 1] - t[0, 8:40, 0]; pl = t[0, 8:40, 2] - t[0, 8:40, 1]
         print("producer: wait halo stage %.0f, issue loads (incl. weight-stage waits) %.0f" % (np.nanmean(pw), np.nanmean(pl)))
         if 4 in roles:
-            g = t[4, 8:40]
-            print("gen: im2col+issue %.0f, wait (stage free & conv1-1 done) %.0f, readback+store %.0f, next patch %.0f" % (
-                np.nanmean(g[:, 1] - g[:, 0]), np.nanmean(g[:, 2] - g[:, 1]), np.nanmean(g[:, 3] - g[:, 2]),
+            g = t[4, 8:40]; h = t[5, 8:40]
+            print("gen: wait (conv1-1 done & stage free) %.0f, build next operand %.0f, read-back + store %.0f, issue next + signal %.0f, loop gap %.0f" % (
+                np.nanmean(g[:, 1] - g[:, 0]), np.nanmean(g[:, 2] - g[:, 1]), np.nanmean(h[:, 2] - g[:, 2]), np.nanmean(g[:, 3] - h[:, 2]),
                 np.nanmean(t[4, 9:41, 0] - g[:, 3])))
+            print("gen detail: first M tile in registers %.0f, its rows stored %.0f, issue of the next item's MMAs %.0f" % (
+                np.nanmean(h[:, 0] - g[:, 2]), np.nanmean(h[:, 1] - h[:, 0]), np.nanmean(h[:, 3] - h[:, 2])))
