@@ -53,8 +53,8 @@ constexpr int kMaxBars = 32;
 constexpr int kMaxCout = 1024;
 
 // conv1-1 fused into conv1-2 (FUSE1): instead of a TMA load, a halo stage is PRODUCED in place by four extra warps.
-// conv1-1 (Cin = 1, 9 taps) runs as an im2col GEMM on the tensor core: A1 = [384 halo pixels (324 used) x K=32]
-// (the 9 taps twice, zero padded) built from the 20x20 uint8 input patch, B1 = [64 x 32] weights split into a high and
+// conv1-1 (Cin = 1, 9 taps) runs as an im2col GEMM on the tensor core: A1 = [384 halo pixels (324 used) x K=16]
+// (the 9 taps and a column of ones, zero padded) built from the 20x20 uint8 input patch, B1 = [64 x 32] weights split into a high and
 // a low 16-bit half (w = hi + lo, so the fp32-accumulated product carries ~22 weight bits: the layer loses nothing
 // against the fp32 CUDA-core version it replaces), 3 x 2 M=128 MMAs into a private TMEM region; the generator warps read it back, add bias, ReLU, zero the pixels outside the tile (Keras
 // 'same' padding of conv1-2) and store 16-bit rows into the halo stage with the TMA's 128-byte swizzle.  The
@@ -453,12 +453,11 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
           c0.x = v[0] | (v[1] << 16); c0.y = v[2] | (v[3] << 16);
           c0.z = v[4] | (v[5] << 16); c0.w = v[6] | (v[7] << 16);
           c1.x = v[8] | (one16 << 16); c1.y = 0u; c1.z = 0u; c1.w = 0u;     // k = 9: ones column, meets the bias row
-          // k = 0..15 meets the high halves of the weights, k = 16..31 the same taps again for the low halves
+          // one K = 16 block per row; it meets the high halves of the weights in the first MMA and the low halves in
+          // the second (issue_first), so the row is written once
           const uint32_t rowa = g_a1 + (uint32_t)pix * 128u;
           st_shared_v4(rowa + (uint32_t)((0 ^ (pix & 7)) << 4), c0);
           st_shared_v4(rowa + (uint32_t)((1 ^ (pix & 7)) << 4), c1);
-          st_shared_v4(rowa + (uint32_t)((2 ^ (pix & 7)) << 4), c0);
-          st_shared_v4(rowa + (uint32_t)((3 ^ (pix & 7)) << 4), c1);
         }
       }
       fence_async_smem();
@@ -480,7 +479,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             const uint32_t d1 = tmem_base + (uint32_t)(kGenTmemCol + mt * 64);
-            const uint64_t ad1 = sdesc_join(sdesc_lo(g_a1 + (uint32_t)(mt * 128 * 128)) + k * 2, hi1);
+            const uint64_t ad1 = sdesc_join(sdesc_lo(g_a1 + (uint32_t)(mt * 128 * 128)), hi1);      // same K block, B advances
             const uint64_t bd1 = sdesc_join(sdesc_lo(g_b1) + k * 2, hi1);
             if (PAIR) umma_f16_2sm(d1, ad1, bd1, idesc1, (uint32_t)k);
             else umma_f16(d1, ad1, bd1, idesc1, (uint32_t)k);
