@@ -332,6 +332,18 @@ def run_postproc(args):
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
+def unet_traffic():
+    """DRAM bytes per image of the U-Net launches from the committed ncu --set full capture (tools/ncu_traffic.py);
+    per image like `achieved`.  None when the capture is not in the tree."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "unet_dram_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        return t["bytes_per_image"], f"{t['what']}; {t['launches']} launches; {t['source']}"
+    except (OSError, KeyError, ValueError):
+        return None, "no ncu capture in profiles/"
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -463,6 +475,7 @@ def run_gpu(args):
         e2e_val = total_images / (e2e_ms_max / 1e3)
         flops_img = spec.unet_flops_per_tile() * TILES_PER_IMAGE
         achieved = flops_img / (stage[1] / 1e3) / 1e12
+        traffic, traffic_note = unet_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -477,8 +490,9 @@ def run_gpu(args):
                     "d2h_bytes_per_step": B * (H * W + 12)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tf_peak, "traffic": None,
-                         "kernel": "k_conv_tc (tcgen05 implicit-GEMM conv, 22 launches per image) = the U-Net stage",
+                         "frac": achieved / tf_peak, "traffic": traffic,
+                         "traffic_note": traffic_note,
+                         "kernel": "k_conv_tc (tcgen05 implicit-GEMM conv, 21 launches per image) + k_head_tc = the U-Net stage",
                          "peak_source": peak_src, "flops_per_image": flops_img, "unet_ms_per_image": float(stage[1])},
             "stage_ms_note": "stages timed on one context running alone (no overlap), 64 images back to back, mean of the last 32",
             "stage_ms_per_image": {"preprocess": float(stage[0]), "unet": float(stage[1]), "stitch": float(stage[2]),
