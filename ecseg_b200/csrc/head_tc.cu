@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_head_tc(const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem), 0);
 
+  grid_dep_launch();     // programmatic dependent launch, see conv_tc.cu
   constexpr int kBlocksPerImg = (kTile / 16) * (kTile / 16);
   const int n_work = p.n_img * kBlocksPerImg;
 
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_head_tc(const __grid_constant__
       tma_load_2d(b_base, &p.tm_b, full_b, 0, 0);
     }
     int sa = 0, pa = 0;
+    grid_dep_wait();     // conv1-4's output (the weights above are constants)
     for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
       const int img = wk / kBlocksPerImg, rem = wk % kBlocksPerImg;
       const int y0 = (rem / (kTile / 16)) << 4, x0 = (rem % (kTile / 16)) << 4;
@@ -212,7 +214,18 @@ int head_tc_launch(ecseg_ctx* ctx, const HeadTcParams& p, cudaStream_t st) {
   }
   const int n_work = p.n_img * (kTile / 16) * (kTile / 16);
   const int grid = n_work < ctx->n_sms ? n_work : ctx->n_sms;
-  k_head_tc<<<grid, kThreads, kSmemBytes, st>>>(p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = getenv("ECSEG_PDL") ? 1 : 0;     // opt-in, see conv_tc.cu
+  ECSEG_CUDA(cudaLaunchKernelEx(&cfg, k_head_tc, p));
   ECSEG_CHECK_LAUNCH();
   return ECSEG_OK;
 }

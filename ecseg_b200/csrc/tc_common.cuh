@@ -330,6 +330,12 @@ __device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity,
   return true;
 }
 
+// Programmatic dependent launch: the next kernel of the stream may start its CTAs (on SMs this grid has already left)
+// once every CTA of this grid has executed launch_dependents; what it reads from this grid it reads after
+// grid_dep_wait(), which returns when this grid has completed and its memory is visible.
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
