@@ -715,8 +715,7 @@ int launch_impl(ecseg_ctx* ctx, ConvTcParams& p, cudaStream_t st) {
   const int n_items = ((n_mblocks + CS - 1) / CS) * p.n_chunks;
   int clusters = ctx->n_sms / CS;
   if (n_items < clusters) clusters = n_items;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * CS);
   cfg.blockDim = dim3(FUSE1 ? kThreads + kGenThreads : kThreads);
   cfg.dynamicSmemBytes = smem;

@@ -214,8 +214,7 @@ int head_tc_launch(ecseg_ctx* ctx, const HeadTcParams& p, cudaStream_t st) {
   }
   const int n_work = p.n_img * (kTile / 16) * (kTile / 16);
   const int grid = n_work < ctx->n_sms ? n_work : ctx->n_sms;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes;

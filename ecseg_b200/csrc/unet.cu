@@ -441,8 +441,8 @@ int unet_load_weights(ecseg_ctx* ctx, const float* blob, size_t n_floats, int pr
       if (tc) {      // the same weights as a [64 cout][32 k] 16-bit GEMM operand (hi | lo halves) for the fused first layer
         std::vector<uint16_t> w16(64 * 32, 0);
         auto h2f = [&](uint16_t u) -> float {
-          if (bf16) { __nv_bfloat16 h; memcpy(&h, &u, 2); return __bfloat162float(h); }
-          __half h; memcpy(&h, &u, 2); return __half2float(h);
+          if (bf16) { __nv_bfloat16_raw r; r.x = u; return __bfloat162float(__nv_bfloat16(r)); }
+          __half_raw r; r.x = u; return __half2float(__half(r));
         };
         for (int co = 0; co < 64; ++co)
           for (int t = 0; t < 9; ++t) {
