@@ -254,8 +254,11 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
             if (leader) mark(0, it * 16 + t + 1);
           }
         } else {
+          // (resident weights: the layer's cin_chunks x 4 view stages are all of the weight stages -- filled for the CTA's
+          //  first item only, the stage index still walks them so every later item finds its views in place)
 #pragma unroll
           for (int v = 0; v < kNumViews; ++v) {
+            if (p.b_resident && it != cluster_id) { if (++sb == BS) { sb = 0; pb ^= 1; } continue; }
             ok = __all_sync(0xffffffffu, mbar_wait(empty_b(sb), pb ^ 1, p.device_error, 2));
             if (!ok) break;
             if (leader && PAIR) {
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
           const uint32_t idesc4 = make_idesc(kM, 4 * N_TILE, BF16), idesc2 = make_idesc(kM, 2 * N_TILE, BF16);
 #pragma unroll
           for (int v = 0; v < kNumViews; ++v) {
-            ok = __all_sync(0xffffffffu, mbar_wait(full_b(sb), pb, p.device_error, 5));
+            if (!p.b_resident || it == cluster_id) ok = __all_sync(0xffffffffu, mbar_wait(full_b(sb), pb, p.device_error, 5));
             if (!ok) break;
             tc_fence_after();
             const uint32_t b_lo = sdesc_lo(b_base + sb * kBStage);
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
                   }
                 }
               }
-              commit_all(empty_b(sb));
+              if (!p.b_resident) commit_all(empty_b(sb));
             }
             __syncwarp();
             if (++sb == BS) { sb = 0; pb ^= 1; }
@@ -700,9 +703,19 @@ int launch_impl(ecseg_ctx* ctx, ConvTcParams& p, cudaStream_t st) {
   // pipeline depths: halo stages first (each covers 9 taps of MMA work), the rest goes to weight stages
   const int budget = 227 * 1024;
   p.a_stages = ((N_TILE == 64 && NACC == 1 && !FUSE1) || NACC == 4) ? 3 : 2;
+  if (NACC == 4 && p.b_resident) p.a_stages = 2;      // room for all of the layer's view stages
   p.b_stages = (budget - smem_bytes(N_TILE, NACC, PAIR, p.a_stages, 0, FUSE1)) / b_stage_bytes(N_TILE, NACC, PAIR);
-  if (p.b_resident && (NACC != 1 || (FUSE1 && !PAIR) || p.cin_chunks != 1 || p.n_chunks != 1 || p.b_stages < 9)) p.b_resident = 0;
-  if (p.b_resident) p.b_stages = 9;      // one stage per tap, filled once
+  // resident weights: conv -- one stage per tap (Cin = 64, one output chunk); transposed conv -- one stage per
+  // (64-channel chunk, halo view), at most 8 (Cin <= 128, one output chunk)
+  const int need = NACC == 1 ? 9 : 4 * p.cin_chunks;
+  if (p.b_resident && ((FUSE1 && !PAIR) || (NACC == 1 && p.cin_chunks != 1) || p.n_chunks != 1 || p.b_stages < need || need > 9)) {
+    p.b_resident = 0;
+    if (NACC == 4) {
+      p.a_stages = 3;
+      p.b_stages = (budget - smem_bytes(N_TILE, NACC, PAIR, p.a_stages, 0, FUSE1)) / b_stage_bytes(N_TILE, NACC, PAIR);
+    }
+  }
+  if (p.b_resident) p.b_stages = need;      // filled once
   else if (p.b_stages > 8) p.b_stages = 8;
   if (p.b_stages < 2 || 2 * p.a_stages + 2 * p.b_stages + 6 > kMaxBars) { ctx->err = "conv_tc: bad pipeline configuration"; return ECSEG_E_INVALID; }
   const int smem = smem_bytes(N_TILE, NACC, PAIR, p.a_stages, p.b_stages, FUSE1);

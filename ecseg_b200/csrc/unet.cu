@@ -633,7 +633,9 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
       p.trace = ctx->trace;
     }
   }
-  p.b_resident = (!l.convT && l.cin == 64 && rows == n_tile && !getenv("ECSEG_NO_RESIDENT_B")) ? 1 : 0;   // conv1-2 (unfused), conv1-4
+  // weights resident in shared memory for the whole kernel: conv1-2, conv1-4 (Cin = 64) and up1 (Cin = 128, 64 outputs)
+  p.b_resident = (((!l.convT && l.cin == 64) || (l.convT && l.cin <= 128 && !getenv("ECSEG_NO_RESIDENT_UP"))) && rows == n_tile &&
+                  !getenv("ECSEG_NO_RESIDENT_B")) ? 1 : 0;
   if (fuse1) {
     p.first_src = net->in_tiles ? net->in_tiles : net->in_pre;
     p.first_from_tiles = net->in_tiles != nullptr;
