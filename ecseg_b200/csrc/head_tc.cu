@@ -169,6 +169,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_head_tc(const __grid_constant__
       }
       tc_fence_before();
       mbar_arrive(tmem_empty(g));             // accumulator drained: the MMAs of this group's next block may start
+      // the tile's position in the grid, once per block (runtime divisions stay out of the per-pixel code)
+      const int tci = p.labels ? img / p.grid.nr : 0, tri = img - tci * p.grid.nr;
+      const int sy = p.labels ? p.grid.start_r(tri) + y0 : 0, sx = p.labels ? p.grid.start_c(tci) + x0 : 0;
       named_bar_sync(1 + g, 128);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -180,16 +183,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_head_tc(const __grid_constant__
           const float4 zt = *reinterpret_cast<const float4*>(zg + ((ty + t / 3) * 18 + tx + t % 3) * kZPitch + t * 4);
           z[0] += zt.x; z[1] += zt.y; z[2] += zt.z; z[3] += zt.w;
         }
-        float pr[4];
-        softmax4(z, pr);
-        const int y = y0 + ty, x = x0 + tx;
-        const size_t pix = ((size_t)img * kTile + y) * kTile + x;
-        if (p.logits) reinterpret_cast<float4*>(p.logits)[pix] = make_float4(z[0], z[1], z[2], z[3]);
-        if (p.probs) reinterpret_cast<float4*>(p.probs)[pix] = make_float4(pr[0], pr[1], pr[2], pr[3]);
+        if (p.logits || p.probs) {
+          float pr[4];
+          softmax4(z, pr);
+          const size_t pix = ((size_t)img * kTile + y0 + ty) * kTile + x0 + tx;
+          if (p.logits) reinterpret_cast<float4*>(p.logits)[pix] = make_float4(z[0], z[1], z[2], z[3]);
+          if (p.probs) reinterpret_cast<float4*>(p.probs)[pix] = make_float4(pr[0], pr[1], pr[2], pr[3]);
+        }
         if (p.labels) {
           int err = 0;
-          const int lab = quantised_argmax(pr[0], pr[1], pr[2], pr[3], &err);
-          stitch_write_owned(p.grid, img, y, x, lab, p.labels);
+          stitch_write_owned_at(p.grid, tri, tci, sy + ty, sx + tx, label_from_logits(z, &err), p.labels);
         }
       }
       named_bar_sync(1 + g, 128);
