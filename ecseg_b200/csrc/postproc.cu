@@ -176,6 +176,8 @@ __global__ void __launch_bounds__(256) k_ccl_tile(const uint8_t* __restrict__ cl
   }
   if (threadIdx.x < 4) s_hist[threadIdx.x] = 0;
   if (threadIdx.x == 0) { s_fg = 0; s_nroots = 0; }
+  __syncthreads();      // the class histogram below is accumulated by every warp: not before warp 0 has cleared it
+                        // (found by running the ragged-shape tests under compute-sanitizer, which reorders the warps)
   const int x = x0 + lane;
   const bool want_c = (what & FIN_CENTROID) != 0;
   const bool want_a = (what & (FIN_AREA | FIN_CENTROID)) != 0;
