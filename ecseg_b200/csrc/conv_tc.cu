@@ -4,28 +4,29 @@
 // inside model.predict_on_batch (call site src/utils.py:115; topology template
 // src/model_layers/models.py:17-136).
 //
-// One persistent CTA per SM, 8 warps, optionally paired into clusters of 2:
-//   warp 0 lane 0 : TMA producer.  Per (M block, 64-channel chunk) ONE halo load of the 18x18
-//                   pixel neighbourhood of a 16x16 output block (TMA zero-fills outside the image
-//                   tile = Keras 'same' padding), and per (chunk, tap) one weight tile
-//                   [N_TILE x 64].  The 9 taps are 9 shifted VIEWS of the same halo in shared
-//                   memory (descriptor start address + (dy*18+dx)*128 B), so activations cross
-//                   L2 -> SM once instead of nine times.  In a cluster each CTA fetches 1/CS of
-//                   every weight tile and multicasts it to all CTAs of the cluster (the CTAs work
-//                   on different M blocks of the same output-channel chunk in lock step), which
-//                   divides the L2 -> SM weight traffic by CS.
-//   warp 1 lane 0 : MMA issuer.  tcgen05.mma.cta_group::1.kind::f16, M=128 x N=N_TILE x K=16,
-//                   two M halves (left / right 8 columns of the 16x16 block) share every weight
-//                   stage; fp32 accumulators live in TMEM (2 x NACC x N_TILE columns per stage,
-//                   double buffered when that fits twice into the 512 columns).  For a transposed
-//                   convolution the 9 taps are routed to NACC = 4 accumulators, one per output
-//                   parity, so the halo is loaded once for all four.
+// One persistent CTA per SM, 12 warps (16 in the fused first layer), launched as CTA pairs (cta_group::2, a cluster of
+// 2) on every layer of the default variant table; single CTAs and multicast clusters remain as debug variants:
+//   warp 0        : TMA producer (whole warp, one elected lane issues).  Per (M block, 64-channel chunk) ONE halo load
+//                   of the 18x18 pixel neighbourhood of a 16x16 output block (TMA zero-fills outside the image tile =
+//                   Keras 'same' padding), and per (chunk, tap) one weight tile [N_TILE x 64].  The 9 taps are 9
+//                   shifted VIEWS of the same halo in shared memory (descriptor start address + (dy*18+dx)*128 B), so
+//                   activations cross L2 -> SM once instead of nine times.  Each CTA of a pair fetches its own halo and
+//                   its half of every weight tile; both signal the leader CTA's barriers.  Layers whose weights fit
+//                   (Cin = 64 convolutions, the Cin = 128 transposed convolution) keep them resident.
+//   warp 1        : MMA issuer (leader CTA of a pair).  tcgen05.mma.cta_group::2.kind::f16, M = 256 over the pair x
+//                   N = N_TILE x K = 16, the two M halves of a block (left / right 8 columns) share every weight stage;
+//                   fp32 accumulators live in TMEM (halves x NACC x N_TILE columns per stage, double buffered when that
+//                   fits twice into the 512 columns).  For a transposed convolution the 9 taps are grouped by the halo
+//                   view they read and routed to NACC = 4 accumulators, one per output parity, so the halo is loaded
+//                   once for all four; it works on 16x8 blocks.
 //   warp 2        : TMEM allocation / deallocation.
-//   warps 4..7    : epilogue.  tcgen05.ld -> bias -> ReLU -> 16-bit pack -> 128B-swizzled staging
-//                   tile in shared memory -> TMA store (cp.async.bulk.tensor) of full 128-byte
-//                   pixel rows into the NHWC destination (a channel slice of a concat buffer, or one
-//                   parity of the 2x up-sampled grid through a strided tensor map); the 2x2 max
-//                   pool of the same tile is reduced with two warp shuffles and stored the same way.
+//   warps 4..11   : epilogue, two groups of four warps alternating over (accumulator, half, 64-channel slab) units.
+//                   tcgen05.ld -> bias -> ReLU folded into the 16-bit conversion -> 128B-swizzled staging tile in
+//                   shared memory -> TMA store (cp.async.bulk.tensor) of full 128-byte pixel rows into the NHWC
+//                   destination (a channel slice of a concat buffer, or one parity of the 2x up-sampled grid through a
+//                   strided tensor map); the 2x2 max pool of the same tile is reduced on the packed 16-bit pairs with
+//                   two warp shuffles and stored the same way.
+//   warps 12..15  : (fused first layer only) conv1-1 generator, see FUSE1 below.
 // Pipelines are mbarrier based (full/empty per A stage, per B stage, per accumulator stage).
 #include "conv_tc.cuh"
 #include "tc_common.cuh"
