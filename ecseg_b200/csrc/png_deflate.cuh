@@ -1,6 +1,6 @@
 // Row-parallel PNG scanline encoder: palette expansion + PNG filter + fixed-Huffman deflate, shared by
 // the CUDA kernel (artifacts.cu: one thread block per scanline) and a sequential host emulation that
-// tests/test_png_host.py drives without a GPU (pngdef_host.cpp).
+// tests/test_artifacts_host.py drives without a GPU (pngdef_host.cpp).
 //
 // Replaces the overlay writer of the reference, plt.imsave(<stem>.png, I, cmap=ListedColormap(4 colours),
 // vmin=0, vmax=4) (src/metaseg.py:47-52): an RGBA8 PNG whose pixels are PALETTE[label].

@@ -23,7 +23,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 // try_wait with a suspend-time hint: the waiting thread is parked by the hardware until the phase completes (or the
 // hint expires) instead of spinning.  Without it, the ~10 waiting warps of a CTA burned half of the SM's issue slots
-// in try_wait loops and slowed the warps that had work (profiles/r01_ncu_fuse1.md).
+// in try_wait loops and slowed the warps that had work (measured while bringing up the fused first layer; that session's ncu capture was not kept).
 constexpr uint32_t kSuspendHintNs = 1000000u;
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;

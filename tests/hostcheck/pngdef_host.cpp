@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE (not part of the product): sequential host execution of the scanline encoder of
 // ecseg_b200/csrc/png_deflate.cuh -- the same token / framing / Adler arithmetic k_png_rows, k_png_scan and
-// k_png_gather run on the GPU, one "thread" at a time -- so tests/test_png_host.py can pin the bit stream
+// k_png_gather run on the GPU, one "thread" at a time -- so tests/test_artifacts_host.py can pin the bit stream
 // against zlib and cv2 without a GPU.  Built by tests/hostcheck/Makefile into libpngdef_host.so.
 #include <stdint.h>
 #include <string.h>
