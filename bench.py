@@ -84,25 +84,31 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # CPU reference arm (the oracle port; the reference's TF/skimage stack is not installable)
 # --------------------------------------------------------------------------------------------
-def cpu_step(oracle_net, img, n_tiles_sample: int):
-    """One bounded sample of the workload on the host cores: the full CPU path on one 2048x2048
-    image, with the U-Net evaluated on `n_tiles_sample` of its 100 tiles (its cost is exactly
-    linear in tiles) and everything else at full size.  Returns seconds per full image."""
+CPU_STAGES = ("preprocess_tile", "unet", "stitch_quantise_argmax", "meta_inference", "count_cc")
+
+
+def cpu_step(oracle_net, img, n_tiles: int = TILES_PER_IMAGE):
+    """The reference's per-image path (src/utils.py:109-120 + src/metaseg.py:46) on the host cores for ONE 2048x2048
+    image, every stage at full size: all 100 tiles go through the U-Net, nothing is extrapolated.  (`n_tiles` < 100
+    is only for the warm-up call.)  Returns (seconds, per-stage seconds)."""
     from oracle import metaseg_oracle as mo
-    t0 = time.perf_counter()
+    t = [time.perf_counter()]
     pre = mo.meta_preprocess(img)
     pos, tiles = mo.im2patches_overlap(pre[..., None])
-    t1 = time.perf_counter()
-    probs_s = oracle_net.predict_on_batch(tiles[:n_tiles_sample])
-    t2 = time.perf_counter()
-    probs = np.broadcast_to(probs_s[:1], (len(tiles),) + probs_s.shape[1:]).copy()
-    probs[:n_tiles_sample] = probs_s
+    t.append(time.perf_counter())
+    probs = oracle_net.predict_on_batch(tiles[:n_tiles])
+    if n_tiles < len(tiles):
+        probs = np.concatenate([probs, np.broadcast_to(probs[:1], (len(tiles) - n_tiles,) + probs.shape[1:])])
+    t.append(time.perf_counter())
+    lab = mo.quantise_argmax(mo.patches2im_overlap(probs, pos))
+    t.append(time.perf_counter())
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        lab = mo.meta_inference(mo.quantise_argmax(mo.patches2im_overlap(probs, pos)))
+        lab = mo.meta_inference(lab)
+        t.append(time.perf_counter())
         mo.count_cc(lab == 3)
-    t3 = time.perf_counter()
-    return (t1 - t0) + (t2 - t1) * (len(tiles) / n_tiles_sample) + (t3 - t2)
+    t.append(time.perf_counter())
+    return t[-1] - t[0], [b - a for a, b in zip(t[:-1], t[1:])]
 
 
 def make_oracle_net():
@@ -113,30 +119,53 @@ def make_oracle_net():
     return UNetOracle(wmod.make_weights(0), batch=4)
 
 
+def workload_config(images_per_step: int, contexts: int, pool: int):
+    """`config` of the bench line -- the same dict on both arms (the reference arm describes its bounded sample of
+    this workload in `cpu_baseline.sample`)."""
+    return {"workload": f"{images_per_step} x 2048x2048 synthetic DAPI images per GPU per step (100 tiles each), "
+                        "whole path: preprocess+tile+U-Net+stitch+meta_inference+count",
+            "weights": "random-init seed 0 of the metaseg.h5 architecture (BN folded)",
+            "contexts_per_gpu": contexts,
+            "l2": "each image moves ~6 GB of activations through HBM, far beyond the 126 MB L2; "
+                  f"{pool} distinct images cycled",
+            "collectives": "none on the data path; torch.distributed (NCCL) only for the start barrier and the "
+                           "max-over-ranks of the timer"}
+
+
 def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path (the oracle port: reference control flow,
+    TensorFlow -> torch-CPU oneDNN fp32, skimage -> scipy; neither library is installable offline) on this box's host
+    cores.  MEASURED, not extrapolated: every step is one whole 2048x2048 image, all 100 tiles through the U-Net.
+    Under torchrun only rank 0 works; the other ranks exit 0."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from ecseg_b200 import synth
     net = make_oracle_net()
-    imgs = [synth.synth_dapi(s, H, W) for s in range(2)]
-    n_sample = args.cpu_tiles
+    imgs = [synth.synth_dapi(1000 + s, H, W) for s in range(2)]
     for i in range(args.warmup):
-        cpu_step(net, imgs[i % 2], n_sample)
-    t = [cpu_step(net, imgs[i % 2], n_sample) for i in range(args.steps)]
-    sec = float(np.mean(t))
+        cpu_step(net, imgs[i % 2])
+    t0 = time.perf_counter()
+    res = [cpu_step(net, imgs[i % 2]) for i in range(args.steps)]
+    wall = time.perf_counter() - t0
+    sec = wall / args.steps
+    stages = np.mean([r[1] for r in res], axis=0)
     val = 1.0 / sec
-    sample = (f"per step: full CPU path on one 2048x2048 image, U-Net on {n_sample} of its 100 tiles and "
-              f"scaled x{100 // n_sample if 100 % n_sample == 0 else round(100 / n_sample, 2)} (cost linear in tiles), "
-              "everything else full size")
+    n_ctx = max(1, args.contexts)
+    sample = ("each step = ONE whole 2048x2048 image of the workload (1 of the GPU arm's "
+              f"{args.images_per_step} images per step), all 100 tiles through the U-Net, every stage at full size; "
+              "nothing extrapolated; rank 0 only (one CPU process whatever --gpus says)")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "1 x 2048x2048 synthetic DAPI image per step (100 tiles)", "weights": "random-init seed 0"},
+        "config": workload_config(args.images_per_step, n_ctx, max(args.images_per_step, 8)),
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference control flow restated (oracle/); TensorFlow -> torch-CPU oneDNN, skimage -> scipy: neither is installable offline",
+        "cpu_stage_s_per_image": {k: float(v) for k, v in zip(CPU_STAGES, stages)},
+        "timed_region_s": wall,
+        "note": "reference control flow restated (oracle/); TensorFlow -> torch-CPU oneDNN, skimage -> scipy: neither is "
+                "installable offline.  One CPU process on rank 0 at every N: compare per-N GPU values with it as context only.",
     }
     print(json.dumps(line), flush=True)
 
@@ -144,7 +173,7 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 # with artefacts: the whole `make metaseg` loop (SURVEY section 8d, config 3 "with artefacts")
 # --------------------------------------------------------------------------------------------
-def run_artifacts(args, weights, local):
+def run_artifacts(args, weights, local, rank=0, barrier=None):
     """TIFF files in -> dapi/<name>.tif + labels/<stem>.png + labels/<stem>.npy out through ecseg_b200.pipeline
     (decode, GPU path with on-device PNG deflate / int64 widening, file writes overlapped), on a bounded sample,
     next to the reference's writer calls timed on the host for the same label maps."""
@@ -166,7 +195,7 @@ def run_artifacts(args, weights, local):
         os.mkdir(os.path.join(d, "dapi"))
         os.mkdir(os.path.join(d, "labels"))
         n = args.artifact_images
-        distinct = [synth.synth_dapi(5000 + s, H, W) for s in range(8)]
+        distinct = [synth.synth_dapi(5000 + 100 * rank + s, H, W) for s in range(8)]
         paths = []
         for i in range(n):
             p = os.path.join(d, f"img{i:04d}.tif")
@@ -176,6 +205,8 @@ def run_artifacts(args, weights, local):
                              n_readers=args.readers, n_writers=args.writers, max_bytes_per_px=1)
         try:
             pipe.run(paths[:8])                       # warm-up: page in buffers, create output files once
+            if barrier:
+                barrier()                             # all ranks start their timed run together (shared host cores)
             rows = pipe.run(paths)
             st = dict(pipe.stats)
         finally:
@@ -212,9 +243,10 @@ def run_artifacts(args, weights, local):
 PP_BYTES_PER_PX = 53      # algorithmic bytes with the two no-op merge_comp passes elided
 
 
-def run_postproc(args):
-    """A step = `--maps-per-step` synthetic 4-class 2048x2048 label maps through meta_inference + count_cc on one
-    GPU, spread over `--pp-contexts` post-processing-only contexts / streams (label maps are independent)."""
+def postproc_line(args, steps=None, cpu_baseline=True):
+    """BASELINE.json config 4.  A step = `--maps-per-step` synthetic 4-class 2048x2048 label maps through
+    meta_inference + count_cc on one GPU, spread over `--pp-contexts` post-processing-only contexts / streams (label
+    maps are independent).  Returns the JSON line as a dict."""
     import torch
     from ctypes import c_void_p
 
@@ -222,14 +254,13 @@ def run_postproc(args):
     from ecseg_b200.engine import Engine
 
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if int(os.environ.get("RANK", "0")) != 0:
-        return
+    steps = steps or args.steps
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     S, B = max(1, args.pp_contexts), args.maps_per_step
     engs = [Engine(local, H, W, max_tiles=0) for _ in range(S)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
-    n_distinct = 16
+    n_distinct = args.pp_distinct
     host_maps = [torch.from_numpy(synth.synth_label_map(s, H, W)).pin_memory() for s in range(n_distinct)]
     pristine = [m.to(dev) for m in host_maps]
     work = [torch.empty((H, W), dtype=torch.uint8, device=dev) for _ in range(B)]      # B x 4 MB cycled; workspace
@@ -269,7 +300,7 @@ def run_postproc(args):
     l0 = sum(e.launch_count() for e in engs)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(); fork()
-    for i in range(args.steps):
+    for i in range(steps):
         step(i * B)
     join(); ev1.record()
     torch.cuda.synchronize()
@@ -279,27 +310,28 @@ def run_postproc(args):
     counts = n_out.cpu().numpy().tolist()
     # one context alone, one map at a time: the per-launch latency view of the same kernels
     ev0.record()
-    for j in range(8):
+    n_single = min(8, B)
+    for j in range(n_single):
         work[j].copy_(pristine[j % n_distinct])
         engs[0]._chk(engs[0].lib.ecseg_postprocess(engs[0].ctx, work[j].data_ptr(), H, W, 0, n_out[j:].data_ptr(),
                                                    px_out[j:].data_ptr(), engs[0]._stream()))
     ev1.record(); torch.cuda.synchronize()
-    ms_single = ev0.elapsed_time(ev1) / 8
+    ms_single = ev0.elapsed_time(ev1) / n_single
     # end to end: pinned host map in, label map + count back on the host
     fork(); step(0, e2e=True); join(); torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(steps):
         fork(); step(i * B, e2e=True); join()
         n_out.cpu()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     _, hbm_peak, peak_src = peaks()
-    maps = B * args.steps
+    maps = B * steps
     value = maps / (ms / 1e3)
     achieved = PP_BYTES_PER_PX * H * W * value / 1e9
     line = {
         "metric": "meta_inference + count_cc label maps/s (2048x2048, BASELINE.json config 4)", "value": value, "unit": "maps/s",
-        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "n_gpus": 1, "steps": steps, "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
         "config": {"workload": f"{B} synthetic 4-class 2048x2048 label maps per step ({n_distinct} distinct, ellipses + discs + 2000 "
                                "salt pixels), fill_holes x2 + size_thresh + boundary erase + nucleus-in-metaphase + dilation + "
@@ -314,7 +346,7 @@ def run_postproc(args):
                      "single_stream_gbs": PP_BYTES_PER_PX * H * W / (ms_single / 1e3) / 1e9},
         "clocks": clocks, "n_ec_first_maps": counts[:4],
     }
-    if not args.no_cpu_baseline:
+    if cpu_baseline and not args.no_cpu_baseline:
         from oracle import metaseg_oracle as mo
         m = host_maps[0].numpy().astype(np.int64)
         t0 = time.perf_counter()
@@ -326,7 +358,15 @@ def run_postproc(args):
         line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "maps/s", "cores": 1, "kind": "port",
                                 "sample": "one 2048x2048 label map through oracle meta_inference (with merge_comp, as the "
                                           "reference runs it) + count_cc", "n_ec": int(ref_n), "gpu_n_ec_same_map": counts[0]}
-    print(json.dumps(line), flush=True)
+    for e in engs:
+        e.close()
+    return line
+
+
+def run_postproc(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    print(json.dumps(postproc_line(args)), flush=True)
 
 
 # --------------------------------------------------------------------------------------------
@@ -381,6 +421,7 @@ def run_gpu(args):
     host_imgs = [torch.from_numpy(synth.synth_dapi(1000 * rank + s, H, W)).pin_memory() for s in range(pool)]
     dev_imgs = [t.to(dev) for t in host_imgs]
     host_labels = [torch.empty((H, W), dtype=torch.uint8).pin_memory() for _ in range(n_ctx)]
+    host_dapi = [torch.empty((H, W), dtype=torch.uint8).pin_memory() for _ in range(n_ctx)]   # utils.py:112 writes it per image
     outs = [(torch.empty((H, W), dtype=torch.uint8, device=dev), torch.empty((H, W), dtype=torch.uint8, device=dev),
              torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int64, device=dev))
             for _ in range(n_ctx)]
@@ -412,7 +453,7 @@ def run_gpu(args):
             if pending[k]:
                 n += engs[k].segment_host_wait()[0]
             with torch.cuda.stream(streams[k]):
-                engs[k].segment_host_async(host_imgs[(i0 + j) % pool].numpy(), host_labels[k].numpy())
+                engs[k].segment_host_async(host_imgs[(i0 + j) % pool].numpy(), host_labels[k].numpy(), host_dapi[k].numpy())
             pending[k] = True
         for k in range(n_ctx):          # every step ends with its results (labels + counts) on the host
             if pending[k]:
@@ -480,14 +521,10 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"{B} x 2048x2048 synthetic DAPI images per GPU per step (100 tiles each), "
-                                   "whole path: preprocess+tile+U-Net+stitch+meta_inference+count",
-                       "weights": "random-init seed 0 of the metaseg.h5 architecture (BN folded)",
-                       "contexts_per_gpu": n_ctx,
-                       "l2": "each image moves ~6 GB of activations through HBM, far beyond the 126 MB L2; "
-                             f"{pool} distinct images cycled"},
+            "config": workload_config(B, n_ctx, pool),
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": B * H * W,
-                    "d2h_bytes_per_step": B * (H * W + 12)},
+                    "d2h_bytes_per_step": B * (2 * H * W + 24),
+                    "what": "pinned host image in; label map + dapi plane (what src/utils.py:112 saves) + count and status words back"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": achieved / tf_peak, "traffic": traffic,
@@ -501,21 +538,99 @@ def run_gpu(args):
                                 "peak_gbs": hbm_peak, "frac": 53 * H * W / (stage[3] / 1e3) / 1e9 / hbm_peak},
             "clocks": clocks, "device_error": dev_err,
         }
-        if world == 1 and args.artifact_images > 0:
-            for e in engs:
-                e.close()
-            line["artifacts"] = run_artifacts(args, weights, local)
+        if world == 1 and not args.no_extras:
+            line["config1_example"] = run_config1(eng, args.precision)
+            line["config5_overlay_chain"] = run_config5(eng)
+    for e in engs:
+        e.close()
+    if args.artifact_images > 0:
+        # BASELINE config 3 "with artefacts": every rank runs the product pipeline over its own TIFF files
+        art = run_artifacts(args, weights, local, rank, barrier)
+        t = torch.tensor([art["wall_s"], float(art["images"])], device=dev, dtype=torch.float64)
+        if world > 1:
+            wall = t[:1].clone(); dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+            tot = t[1:].clone(); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            art["images"] = int(tot.item()); art["wall_s"] = float(wall.item())
+            art["value"] = art["images"] / art["wall_s"]
+            art["what"] += f"; {world} ranks, one pipeline per GPU, whole-job images / slowest rank's wall time"
+        if rank == 0:
+            line["artifacts"] = art
+    if rank == 0:
+        if world == 1 and not args.no_extras:
+            pl = postproc_line(args, steps=max(1, args.pp_maps // args.maps_per_step), cpu_baseline=False)
+            line["config4_postproc"] = {k: pl[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "e2e", "gpu_launches",
+                                                           "roofline", "n_ec_first_maps")}
         if world == 1 and not args.no_cpu_baseline:
             net = make_oracle_net()
             img = host_imgs[0].numpy()
             cpu_step(net, img, 2)
-            sec = cpu_step(net, img, args.cpu_tiles)
+            sec, stages = cpu_step(net, img)
             line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"one 2048x2048 image, U-Net on {args.cpu_tiles} of 100 tiles scaled "
-                                              "linearly, rest of the path full size (oracle/, torch-CPU fp32)"}
+                                    "sample": "ONE whole 2048x2048 image of the workload through the oracle port (oracle/, "
+                                              "torch-CPU fp32 U-Net on all 100 tiles, scipy post-processing), after a 2-tile warm-up",
+                                    "cpu_stage_s_per_image": {k: float(v) for k, v in zip(CPU_STAGES, stages)}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_config1(eng, precision):
+    """BASELINE config 1 as an extra of the bench line: input.tif := 255 - example_ecSeg/dapi.jpeg (1040x1392, 35 tiles;
+    pixels frozen in tests/golden/example.npz together with what the reference's utils.meta_segment returned for it with
+    the fp32 CPU U-Net) through the whole GPU path: throughput, label agreement, count."""
+    import torch
+    path = os.path.join(ROOT, "tests", "golden", "example.npz")
+    if not os.path.isfile(path):
+        return {"unavailable": "tests/golden/example.npz missing"}
+    g = np.load(path)
+    img = np.ascontiguousarray(g["input"])
+    h, w = img.shape
+    notie = np.unpackbits(g["notie"])[: h * w].reshape(h, w).astype(bool)
+    pinned = torch.from_numpy(img).pin_memory()
+    out = torch.empty((h, w), dtype=torch.uint8).pin_memory()
+    n_ec = 0
+    for _ in range(3):
+        eng.segment_host_async(pinned.numpy(), out.numpy()); n_ec = eng.segment_host_wait()[0]
+    reps = 24
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        eng.segment_host_async(pinned.numpy(), out.numpy()); eng.segment_host_wait()
+    dt = (time.perf_counter() - t0) / reps
+    pre, _ = eng.preprocess(img)
+    raw = eng.stitch_argmax(eng.unet_forward(eng.tile(pre)), h, w).cpu().numpy()
+    return {"workload": "255 - example_ecSeg/dapi.jpeg, 1040x1392 u8, 35 tiles, seed-0 weights", "images_per_s_e2e": 1.0 / dt,
+            "ms_per_image_e2e": dt * 1e3, "contexts": 1, "precision": precision,
+            "label_agreement_vs_reference_run": float((raw == g["raw"])[notie].mean()),
+            "label_agreement_note": "raw (pre-meta_inference) label map vs the reference's utils.meta_segment flow run with the "
+                                    "fp32 CPU U-Net (tests/golden/example.npz), quantised top-2 ties excluded",
+            "n_ec": int(n_ec), "n_ec_reference_run": int(g["count"][0]),
+            "final_map_equal_px_frac": float((out.numpy() == g["final"]).mean())}
+
+
+def run_config5(eng):
+    """BASELINE config 5 as an extra: metaseg followed by meta_overlay (src/meta_overlay.py:59-83) on synthetic RGB
+    DAPI + green / red FISH images, chained on the GPU (the label map never leaves it)."""
+    import torch
+    from ecseg_b200 import synth
+    dev = eng.device
+    imgs = [torch.from_numpy(synth.synth_fish(900 + s, H, W)).to(dev) for s in range(4)]
+    res = None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    t_seg = t_ov = 0.0
+    reps = 8
+    for i in range(reps + 2):
+        im = imgs[i % 4]
+        ev[0].record()
+        labels, _dapi, _n, _px = eng.segment_device(im, H, W, 3, 1)
+        ev[1].record()
+        res = eng.overlay_counts(im, labels, 85)          # syncs (reads the 12 counts back)
+        ev[2].record(); torch.cuda.synchronize()
+        if i >= 2:
+            t_seg += ev[0].elapsed_time(ev[1]); t_ov += ev[1].elapsed_time(ev[2])
+    return {"workload": "2048x2048 RGB u8 (DAPI in B, FISH in G/R), color_sensitivity 85: ecseg_segment_image then "
+                        "ecseg_overlay_counts on the same device buffers", "metaseg_ms_per_image": t_seg / reps,
+            "meta_overlay_ms_per_image": t_ov / reps, "images_per_s_chain": 1e3 * reps / (t_seg + t_ov),
+            "last_counts": res}
 
 
 def main():
@@ -527,7 +642,9 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("ECSEG_PRECISION", "fp16"), choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--images-per-step", type=int, default=8)
     ap.add_argument("--contexts", type=int, default=2, help="library contexts (CUDA streams) per GPU")
-    ap.add_argument("--cpu-tiles", type=int, default=10, help="tiles per CPU sample (of 100)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config 1 / 4 / 5 extras of the bench line")
+    ap.add_argument("--pp-maps", type=int, default=4096, help="label maps of the config-4 extra (BASELINE: 4096)")
+    ap.add_argument("--pp-distinct", type=int, default=64, help="distinct synthetic label maps cycled in the config-4 runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stage-images", type=int, default=64, help="images of the per-stage (roofline) measurement")
     ap.add_argument("--workload", default="metaseg", choices=["metaseg", "postproc"],

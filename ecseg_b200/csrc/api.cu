@@ -1,6 +1,7 @@
 // C ABI of libecseg_b200.so (include/ecseg_b200.h): context lifetime and the entry points the
 // reference-facing Python shim binds.  No exceptions cross this boundary.
 #include <algorithm>
+#include <cstddef>
 #include <cstring>
 #include <new>
 
@@ -27,6 +28,16 @@ static int check_hw(ecseg_ctx* ctx, int h, int w, const char* who) {
     return ECSEG_E_INVALID;
   }
   return ECSEG_OK;
+}
+
+static_assert(offsetof(Counters, device_error) == offsetof(Counters, range_error) + 4 &&
+              offsetof(Counters, act_overflow) == offsetof(Counters, range_error) + 8, "HostResult::status mirrors three adjacent counters");
+
+// the 16-bit range guard of the tensor-core epilogues fired: `layer1` = 1 + index of the first overflowing layer
+static int overflow_error(ecseg_ctx* ctx, int layer1) {
+  ctx->err = "U-Net layer " + std::to_string(layer1 - 1) + " produced values outside the 16-bit operand range (inf / NaN after the "
+             "fp16 conversion): load the weights with precision bf16 or fp32";
+  return ECSEG_E_RANGE;
 }
 
 extern "C" {
@@ -124,6 +135,8 @@ int ecseg_tile(ecseg_ctx* ctx, const uint8_t* d_pre, int h, int w, uint8_t* d_ti
 int ecseg_unet_forward(ecseg_ctx* ctx, const uint8_t* d_tiles, int n, float* d_probs, float* d_logits, void* stream) {
   API_GUARD(ctx);
   if (!d_tiles) { ctx->err = "ecseg_unet_forward: null tiles"; return ECSEG_E_INVALID; }
+  // the staged call has no pre-processing stage in front of it to clear the status counters
+  ECSEG_CUDA(cudaMemsetAsync(&ctx->counters->range_error, 0, 12, (cudaStream_t)stream));
   return unet_forward(ctx, d_tiles, nullptr, nullptr, n, d_probs, d_logits, nullptr, (cudaStream_t)stream);
 }
 
@@ -239,7 +252,7 @@ int ecseg_segment_image_host_async(ecseg_ctx* ctx, const void* h_img, int h, int
   if (h_dapi) ECSEG_CUDA(cudaMemcpyAsync(h_dapi, ctx->dapi, n_px, cudaMemcpyDeviceToHost, st));
   ECSEG_CUDA(cudaMemcpyAsync(&ctx->h_result->n_ec, ctx->d_n_ec, 4, cudaMemcpyDeviceToHost, st));
   ECSEG_CUDA(cudaMemcpyAsync(&ctx->h_result->ec_px, ctx->d_ec_px, 8, cudaMemcpyDeviceToHost, st));
-  ECSEG_CUDA(cudaMemcpyAsync(&ctx->h_result->device_error, &ctx->counters->device_error, 4, cudaMemcpyDeviceToHost, st));
+  ECSEG_CUDA(cudaMemcpyAsync(ctx->h_result->status, &ctx->counters->range_error, 12, cudaMemcpyDeviceToHost, st));
   ECSEG_CUDA(cudaEventRecord(ctx->ev_done, st));
   ctx->pending = true;
   return ECSEG_OK;
@@ -250,10 +263,12 @@ int ecseg_segment_image_host_wait(ecseg_ctx* ctx, int32_t* n_ec, int64_t* ec_px)
   if (!ctx->pending) { ctx->err = "ecseg_segment_image_host_wait: nothing in flight"; return ECSEG_E_STATE; }
   ECSEG_CUDA(cudaEventSynchronize(ctx->ev_done));
   ctx->pending = false;
-  if (ctx->h_result->device_error) {
-    ctx->err = "tcgen05 pipeline watchdog fired (code " + std::to_string(ctx->h_result->device_error) + ")";
+  if (ctx->h_result->status[1]) {
+    ctx->err = "tcgen05 pipeline watchdog fired (code " + std::to_string(ctx->h_result->status[1]) + ")";
     return ECSEG_E_DEVICE;
   }
+  if (ctx->h_result->status[2]) return overflow_error(ctx, ctx->h_result->status[2]);
+  if (ctx->h_result->status[0]) { ctx->err = "Images of type float must be between -1 and 1."; return ECSEG_E_RANGE; }
   if (n_ec) *n_ec = ctx->h_result->n_ec;
   if (ec_px) *ec_px = ctx->h_result->ec_px;
   return ECSEG_OK;
@@ -370,7 +385,7 @@ int ecseg_segment_image_files_async(ecseg_ctx* ctx, const void* h_img, int h, in
   if (h_labels) ECSEG_CUDA(cudaMemcpyAsync(h_labels, ctx->labels, n_px, cudaMemcpyDeviceToHost, st));
   ECSEG_CUDA(cudaMemcpyAsync(&ctx->h_result->n_ec, ctx->d_n_ec, 4, cudaMemcpyDeviceToHost, st));
   ECSEG_CUDA(cudaMemcpyAsync(&ctx->h_result->ec_px, ctx->d_ec_px, 8, cudaMemcpyDeviceToHost, st));
-  ECSEG_CUDA(cudaMemcpyAsync(&ctx->h_result->device_error, &ctx->counters->device_error, 4, cudaMemcpyDeviceToHost, st));
+  ECSEG_CUDA(cudaMemcpyAsync(ctx->h_result->status, &ctx->counters->range_error, 12, cudaMemcpyDeviceToHost, st));
   ECSEG_CUDA(cudaEventRecord(ctx->ev_done, st));
   ctx->pending = true;
   return ECSEG_OK;
@@ -424,6 +439,16 @@ int ecseg_device_error(ecseg_ctx* ctx, int* code) {
   ECSEG_CUDA(cudaDeviceSynchronize());
   ECSEG_CUDA(cudaMemcpy(code, &ctx->counters->device_error, 4, cudaMemcpyDeviceToHost));
   return ECSEG_OK;
+}
+
+int ecseg_activation_overflow(ecseg_ctx* ctx, int* layer) {
+  API_GUARD(ctx);
+  if (!layer) { ctx->err = "ecseg_activation_overflow: null pointer"; return ECSEG_E_INVALID; }
+  int v = 0;
+  ECSEG_CUDA(cudaDeviceSynchronize());
+  ECSEG_CUDA(cudaMemcpy(&v, &ctx->counters->act_overflow, 4, cudaMemcpyDeviceToHost));
+  *layer = v - 1;
+  return v ? overflow_error(ctx, v) : ECSEG_OK;
 }
 
 int ecseg_last_stage_ms(ecseg_ctx* ctx, float ms[4]) {

@@ -35,8 +35,9 @@ struct Counters {
   int n_chrom;                     // compacted chromosome centroids
   int n_nuc;                       // compacted nucleus roots
   int last_root;                   // merge_comp: highest component root (raster-last component)
-  int range_error;                 // img_as_ubyte range violation seen
+  int range_error;                 // img_as_ubyte range violation seen (a probability outside [-1, 1], or NaN)
   int device_error;                // tcgen05 pipeline watchdog
+  int act_overflow;                // 1 + index of the first U-Net layer whose 16-bit output held an inf / NaN (0 = none)
   int ov_hits[4];                  // meta_overlay: components flagged per colocalisation test
   int progress[8];                 // tcgen05 pipeline progress markers (ecseg_debug_progress; written by one thread per role)
   // per labelling run, double buffered by run parity (a run clears the other parity's slots for the next run)
@@ -100,7 +101,8 @@ struct ecseg_ctx {
   int64_t* d_ec_px = nullptr;
 
   // pinned result slot + completion event of the asynchronous host entry
-  struct HostResult { int32_t n_ec; int32_t device_error; int64_t ec_px; uint32_t png_zlib_bytes; uint32_t png_adler; };
+  // status[3] mirrors Counters::{range_error, device_error, act_overflow} (adjacent: one copy)
+  struct HostResult { int32_t n_ec; int32_t status[3]; int64_t ec_px; uint32_t png_zlib_bytes; uint32_t png_adler; };
   HostResult* h_result = nullptr;
   cudaEvent_t ev_done = nullptr;
   bool pending = false;

@@ -597,6 +597,10 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
     int as = 0, pacc = 0;
     bool ok = true;
     int kit = 0;
+    // 16-bit range guard: running maximum of this thread's output magnitudes as unsigned 16-bit patterns (for
+    // non-negative halves the fp16 / bf16 order is the integer order).  An exponent of all ones -- inf from the
+    // conversion's overflow, or a NaN -- shows as a pattern >= 0x7C00 (fp16) / 0x7F80 (bf16); checked once, below.
+    uint32_t mx = 0;
     for (int it = cluster_id; it < n_items && ok; it += n_clusters, ++kit) {
       if (e0) stamp(2 + eg, kit, 0);
       const int mg = it % n_mgroups, nch = it / n_mgroups;
@@ -637,10 +641,10 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
               uint32_t o[16];     // ReLU (models.py:20) rides on the 16-bit conversion
               if (p.relu) {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) o[k] = pack2_relu(f[2 * k], f[2 * k + 1], BF16);
+                for (int k = 0; k < 16; ++k) { o[k] = pack2_relu(f[2 * k], f[2 * k + 1], BF16); mx = __vmaxu2(mx, o[k]); }
               } else {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) o[k] = pack2(f[2 * k], f[2 * k + 1], BF16);
+                for (int k = 0; k < 16; ++k) { o[k] = pack2(f[2 * k], f[2 * k + 1], BF16); mx = __vmaxu2(mx, o[k] & 0x7fff7fffu); }
               }
 #pragma unroll
               for (int k = 0; k < 4; ++k)
@@ -686,6 +690,10 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
       if (++as == kAccStages) { as = 0; pacc ^= 1; }
     }
     if (e0) bulk_wait<0>();
+    {
+      constexpr uint32_t kExpAllOnes = BF16 ? 0x7F80u : 0x7C00u;
+      if (((mx & 0xffffu) >= kExpAllOnes || (mx >> 16) >= kExpAllOnes) && p.act_overflow) atomicCAS(p.act_overflow, 0, p.layer_id);
+    }
   }
 
   tc_fence_before();

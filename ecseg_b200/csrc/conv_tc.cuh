@@ -38,6 +38,8 @@ struct ConvTcParams {
   int b_resident;         // request: keep the layer's 9 weight tap tiles in shared memory for the whole kernel (needs
                           // Cin == 64 and Cout == N_TILE; the launcher clears it when they do not fit)
   int* device_error;      // watchdog flag (Counters::device_error)
+  int* act_overflow;      // Counters::act_overflow: set to layer_id by the first layer whose 16-bit output holds an inf / NaN
+  int layer_id;           // 1 + layer index (spec.UNET_LAYERS)
   int* progress;          // Counters::progress (nullable): role progress markers of CTA 0 for ecseg_debug_progress
   long long* trace;       // nullable: clock64 stamps of CTA 0, [role kTraceRoles][item kTraceItems][stamp 4] (ecseg_debug_trace)
   // conv1-1 fused in front of this layer (conv1-2 only; first_src == nullptr: off).  The halo stages are then computed
@@ -64,6 +66,7 @@ struct HeadTcParams {
   uint8_t* labels;   // [h,w] nullable (needs grid)
   TileGrid grid;
   int* device_error;
+  int* range_error;  // Counters::range_error: a probability outside [-1, 1] or NaN (img_as_ubyte raises, src/utils.py:117)
 };
 int head_tc_launch(ecseg_ctx* ctx, const HeadTcParams& p, cudaStream_t st);
 

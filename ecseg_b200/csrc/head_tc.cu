@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_head_tc(const __grid_constant__
         if (p.labels) {
           int err = 0;
           stitch_write_owned_at(p.grid, tri, tci, sy + ty, sx + tx, label_from_logits(z, &err), p.labels);
+          if (err && p.range_error) *p.range_error = 1;      // NaN / out-of-range probability: img_as_ubyte raises
         }
       }
       named_bar_sync(1 + g, 128);

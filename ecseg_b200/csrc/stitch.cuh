@@ -37,7 +37,7 @@ __device__ __forceinline__ int quantised_argmax(float p0, float p1, float p2, fl
   int best = 0, bq = -1;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    if (p[c] < -1.0f || p[c] > 1.0f) *range_err = 1;
+    if (!(p[c] >= -1.0f && p[c] <= 1.0f)) *range_err = 1;      // written so that a NaN trips it too
     int q = __double2int_rn(__dmul_rn((double)p[c], 255.0));
     q = min(max(q, 0), 255);
     if (q > bq) { bq = q; best = c; }

@@ -221,6 +221,7 @@ struct ConvF32Params {
   float* out; int out_H, out_W, out_pitch, out_choff;
   int head;
   float* probs; float* logits; uint8_t* labels; TileGrid grid;
+  int* range_error;
 };
 
 __global__ void __launch_bounds__(256) k_conv_fp32(const ConvF32Params p) {
@@ -289,6 +290,7 @@ __global__ void __launch_bounds__(256) k_conv_fp32(const ConvF32Params p) {
       if (p.labels) {
         int err = 0;
         stitch_write_owned(p.grid, img, y, x, quantised_argmax(pr[0], pr[1], pr[2], pr[3], &err), p.labels);
+        if (err && p.range_error) *p.range_error = 1;
       }
     } else {
       const int oy = y * p.oscale + p.par_oy[par], ox = x * p.oscale + p.par_ox[par];
@@ -432,6 +434,19 @@ int unet_load_weights(ecseg_ctx* ctx, const float* blob, size_t n_floats, int pr
       ECSEG_CUDA(cudaMalloc(&net->b[li], l.cout * sizeof(float)));
       ECSEG_CUDA(cudaMemcpy(net->b[li], fb.data(), l.cout * sizeof(float), cudaMemcpyHostToDevice));
     }
+    if (li == 0 && precision == ECSEG_PREC_FP16) {
+      // conv1-1's input is bounded (uint8 0..255, src/utils.py:113-115), so its output range is known at load time:
+      // the fused first layer writes it as fp16 without a run-time check (the other layers carry one, conv_tc.cu)
+      for (int co = 0; co < l.cout; ++co) {
+        double s = std::fabs((double)fb[co]);
+        for (int t = 0; t < 9; ++t) s += 255.0 * std::fabs((double)kval(t, 0, co));
+        if (!(s < 65504.0)) {
+          ctx->err = "load_weights: conv1-1 channel " + std::to_string(co) + " can reach " + std::to_string(s) +
+                     " > 65504 (fp16 range) on 0..255 input: use precision bf16 or fp32 for this checkpoint";
+          return ECSEG_E_RANGE;
+        }
+      }
+    }
     if (li == 0) {   // [9][64] fp32 for the CUDA-core first layer
       std::vector<float> w(9 * 64);
       for (int t = 0; t < 9; ++t) for (int co = 0; co < 64; ++co) w[t * 64 + co] = kval(t, 0, co);
@@ -532,6 +547,7 @@ static int run_layer_fp32(ecseg_ctx* ctx, int li, int n, float* d_probs, float* 
   p.head = li == 22;
   if (p.head) {
     p.probs = d_probs; p.logits = d_logits; p.labels = d_labels;
+    p.range_error = &ctx->counters->range_error;
     if (grid) p.grid = *grid;
   } else {
     p.out = (float*)net->buf[wr.out]; p.out_H = out_hw; p.out_W = out_hw;
@@ -560,6 +576,7 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
     h.probs = d_probs; h.logits = d_logits; h.labels = d_labels;
     if (grid) h.grid = *grid;
     h.device_error = &ctx->counters->device_error;
+    h.range_error = &ctx->counters->range_error;
     return head_tc_launch(ctx, h, st);
   }
   ConvTcParams p;
@@ -625,6 +642,8 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   p.out_choff = wr.choff;
   p.bias = net->b[li]; p.relu = l.relu; p.is_bf16 = bf16;
   p.device_error = &ctx->counters->device_error;
+  p.act_overflow = &ctx->counters->act_overflow;
+  p.layer_id = li + 1;
   p.progress = ctx->counters->progress;
   if (const char* e = getenv("ECSEG_TRACE_LAYER")) {       // pipeline trace of one layer (tools/trace_layer.py)
     if (atoi(e) == li) {

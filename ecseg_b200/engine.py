@@ -95,6 +95,13 @@ class Engine:
         self._chk(self.lib.ecseg_device_error(self.ctx, byref(code)))
         return code.value
 
+    def activation_overflow(self) -> int:
+        """Index of the first U-Net layer whose 16-bit output held an inf / NaN in the last forward (-1: none).
+        Raises EcsegError(ECSEG_E_RANGE) when one did -- the fp16 range guard of the tensor-core modes."""
+        layer = c_int()
+        self._chk(self.lib.ecseg_activation_overflow(self.ctx, byref(layer)))
+        return layer.value
+
     def launch_count(self) -> int:
         return int(self.lib.ecseg_launch_count(self.ctx))
 

@@ -21,23 +21,40 @@ from .engine import Engine, tile_grid
 NUM_CLASSES = spec.NUM_CLASSES
 EC_SIZE_THRESHOLD = spec.EC_SIZE_THRESHOLD
 
-_engine = None
+_engines: dict = {}      # CUDA device index -> Engine
 
 
-def default_engine(max_h: int = 2048, max_w: int = 2048) -> Engine:
-    """Process-wide engine on the current CUDA device, grown on demand."""
-    global _engine
-    if _engine is None or _engine.max_h * _engine.max_w < max_h * max_w or \
-            _engine.max_tiles < len(tile_grid(max(max_h, 256), max(max_w, 256))[0]):
+def default_engine(max_h: int = 2048, max_w: int = 2048, device: int | None = None) -> Engine:
+    """Per-process engine on `device` (default: torch's CURRENT CUDA device, so that a rank that called
+    torch.cuda.set_device(local_rank) stays on its own GPU), created on first use and regrown when an image is
+    taller OR wider than what it was sized for."""
+    import torch
+    if device is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("ecseg_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        device = torch.cuda.current_device()
+    max_h, max_w = max(max_h, 256), max(max_w, 256)
+    eng = _engines.get(device)
+    if eng is None or eng.max_h < max_h or eng.max_w < max_w:
         keep = None
-        if _engine is not None:
-            keep = (_engine._weights, _engine.precision) if getattr(_engine, "_weights", None) else None
-            _engine.close()
-        _engine = Engine(0, max(max_h, 256), max(max_w, 256))
+        if eng is not None:
+            keep = (eng._weights, eng.precision) if getattr(eng, "_weights", None) else None
+            max_h, max_w = max(max_h, eng.max_h), max(max_w, eng.max_w)
+            eng.close()
+        eng = Engine(device, max_h, max_w)
         if keep:
-            _engine.load_weights(*keep)
-            _engine._weights = keep[0]
-    return _engine
+            eng.load_weights(*keep)
+            eng._weights = keep[0]
+        _engines[device] = eng
+    return eng
+
+
+def close_engines() -> None:
+    """Release every cached engine (its ~7 GB of activation workspace) -- used before handing the GPU to the
+    overlapped pipeline's own contexts."""
+    for eng in _engines.values():
+        eng.close()
+    _engines.clear()
 
 
 def meta_preprocess(img: np.ndarray) -> np.ndarray:

@@ -17,7 +17,7 @@ import yaml
 
 from . import spec
 from .shard import write_csv
-from .utils import count_cc, get_imgs, load_model, meta_segment  # noqa: F401
+from .utils import allow_random_weights, count_cc, get_imgs, load_model, meta_segment  # noqa: F401
 
 MODEL_NAME = 'metaseg.h5'
 _PALETTE_BGRA = np.array([[p[2], p[1], p[0], p[3]] for p in spec.PALETTE], np.uint8)
@@ -49,7 +49,8 @@ def main(argv):
 
     import torch
     print([torch.cuda.get_device_name(i) for i in range(torch.cuda.device_count())])
-    model = load_model(MODEL_NAME, var.get('precision') if isinstance(var, dict) else None)
+    opt = var if isinstance(var, dict) else {}
+    model = load_model(MODEL_NAME, opt.get('precision'), allow_random_weights(opt))
 
     image_paths = get_imgs(inpath)
     rows = []
@@ -62,7 +63,6 @@ def main(argv):
         from . import tiffio
         from .pipeline import FilesPipeline
         shapes = [tiffio.probe(p) or _shape_of(p) for p in tifs]
-        opt = var if isinstance(var, dict) else {}
         pipe = FilesPipeline(model.weights, model.precision, max(max(s[0] for s in shapes), 256),
                              max(max(s[1] for s in shapes), 256), n_ctx=int(opt.get('contexts', 2)),
                              n_readers=int(opt.get('readers', 4)), n_writers=int(opt.get('writers', 6)),
@@ -90,6 +90,9 @@ def main(argv):
     csv_path = os.path.join(path_split[0], 'ec_quantification.csv')
     print("Saving ec quantification to", csv_path)
     write_csv(csv_path, rows)
+    if model.synthetic:
+        print(f"[ecseg_b200] WARNING: {csv_path} and labels/* were produced with RANDOM-INIT weights (opt-in), "
+              "not with a trained metaseg checkpoint.", file=sys.stderr)
 
 
 if __name__ == "__main__":

@@ -36,6 +36,17 @@ class _Slot:
         self.view = None
 
 
+def _get_or_stop(q: "queue.Queue", stop: threading.Event):
+    """q.get() that gives up (returns None) once `stop` is set: no thread of the pipeline may block forever on a
+    queue whose producer has died (a writer hitting ENOSPC, a GPU call raising, a reader failing to decode)."""
+    while True:
+        try:
+            return q.get(timeout=0.2)
+        except queue.Empty:
+            if stop.is_set():
+                return None
+
+
 def output_paths(image_path: str):
     """(dapi/<name>, labels/<stem>.png, labels/<stem>.npy) exactly as src/utils.py:122-123 / src/metaseg.py:44-53."""
     d, name = os.path.split(image_path)
@@ -88,7 +99,9 @@ class FilesPipeline:
                     i, p = todo_q.get_nowait()
                 except queue.Empty:
                     return
-                slot = free_q.get()
+                slot = _get_or_stop(free_q, stop)
+                if slot is None:
+                    return
                 try:
                     t0 = time.perf_counter()
                     slot.view = tiffio.read_into(p, slot.img)
@@ -148,7 +161,7 @@ class FilesPipeline:
         try:
             k = 0
             for _ in range(n):
-                item = decoded_q.get()
+                item = _get_or_stop(decoded_q, stop)     # None: a reader posted its failure, or a worker set `stop`
                 if item is None or stop.is_set():
                     break
                 i, p, slot = item
@@ -168,6 +181,14 @@ class FilesPipeline:
             errors.append(e)
             stop.set()
         finally:
+            if errors:      # leave the contexts reusable: drain whatever is still in flight, keep the first error
+                for kk, fl in enumerate(inflight):
+                    if fl is not None:
+                        try:
+                            self.engines[kk].segment_files_wait()
+                        except BaseException:  # noqa: BLE001
+                            pass
+                        inflight[kk] = None
             for _ in writers:
                 write_q.put(None)
             for t in writers:

@@ -99,7 +99,7 @@ def main(argv=None) -> int:
     torch.cuda.set_device(local)
 
     from . import metaseg as ms
-    from .utils import get_imgs, load_model, meta_segment
+    from .utils import allow_random_weights, get_imgs, load_model, meta_segment
 
     for sub in ('dapi', 'labels'):
         os.makedirs(os.path.join(inpath, sub), exist_ok=True)
@@ -110,7 +110,7 @@ def main(argv=None) -> int:
     paths = paths[0]
     if not paths:
         raise NameError("name 'path_split' is not defined")   # what the reference does on an empty folder
-    model = load_model(ms.MODEL_NAME, var.get('precision'))
+    model = load_model(ms.MODEL_NAME, var.get('precision'), allow_random_weights(var))
 
     def process_one(p: str) -> int:
         print(f"[rank {rank}] Processing image: ", p)
@@ -144,6 +144,9 @@ def main(argv=None) -> int:
         csv_path = os.path.join(inpath, 'ec_quantification.csv')
         print("Saving ec quantification to", csv_path)
         write_csv(csv_path, rows)
+        if model.synthetic:
+            print(f"[ecseg_b200] WARNING: {csv_path} and labels/* were produced with RANDOM-INIT weights (opt-in), "
+                  "not with a trained metaseg checkpoint.", file=sys.stderr)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -18,10 +18,12 @@ class MetasegModel:
     """What utils.load_model returns: the Keras-model surface the path uses (predict_on_batch),
     plus the fused whole-image call."""
 
-    def __init__(self, weights: dict, precision: str = "fp16"):
+    def __init__(self, weights: dict, precision: str = "fp16", synthetic: bool = False):
         self.weights = weights
         self.precision = precision
-        self._bind(default_engine())
+        self.synthetic = synthetic      # True: seeded random-init weights, not a trained checkpoint
+        # the engine is bound on first use (predict_on_batch / segment): a run that only feeds the overlapped
+        # pipeline (ecseg_b200/pipeline.py, which owns its contexts) never allocates an unused one
 
     def _bind(self, eng):
         if getattr(eng, "_weights", None) is not self.weights or eng.precision != self.precision:
@@ -49,14 +51,25 @@ class MetasegModel:
         return labels, dapi, n, px
 
 
-def load_model(model_name: str, precision: str | None = None) -> MetasegModel:
-    """Reference: tf.keras.models.load_model('models/<name>') (src/utils.py:27-33).  Here the
-    weights come from models/<stem>.npz (ecseg_b200.weights layout); when the file is absent the
-    seeded random-init weights of the same architecture are used (the Mendeley checkpoint is not
-    redistributable offline) and a notice is printed."""
+def allow_random_weights(opt=None) -> bool:
+    """Random-init weights are an explicit opt-in: ECSEG_ALLOW_RANDOM_WEIGHTS=1 (bench, tests) or
+    `allow_random_weights: true` under config.yaml's `metaseg:` key."""
+    if os.environ.get("ECSEG_ALLOW_RANDOM_WEIGHTS", "") not in ("", "0"):
+        return True
+    return bool(isinstance(opt, dict) and opt.get("allow_random_weights"))
+
+
+def load_model(model_name: str, precision: str | None = None, allow_random: bool | None = None) -> MetasegModel:
+    """Reference: tf.keras.models.load_model('models/<name>') (src/utils.py:27-33), which raises when the
+    checkpoint is missing -- so does this.  Weights come from models/<stem>.npz (ecseg_b200.weights layout) or
+    are imported once from the reference's own models/<name> Keras file.  Seeded random-init weights of the same
+    architecture (the Mendeley checkpoint is not redistributable offline) are used ONLY on explicit opt-in
+    (allow_random_weights()), and every result file of such a run is announced as synthetic on stderr."""
+    import sys
     precision = precision or os.environ.get("ECSEG_PRECISION", "fp16")
     path = wmod.default_weights_path(model_name)
     h5 = os.path.join("models", model_name)
+    synthetic = False
     if os.path.isfile(path):
         w = wmod.load_npz(path)
     elif model_name.endswith(".h5") and os.path.isfile(h5):
@@ -65,10 +78,17 @@ def load_model(model_name: str, precision: str | None = None) -> MetasegModel:
         w = keras_import.load_keras_h5(h5)          # ImportError (h5py) / ArchitectureMismatch propagate loudly
         wmod.save_npz(path, w)
         print(f"[ecseg_b200] imported {h5} -> {path}")
-    else:
-        print(f"[ecseg_b200] {path} not found: using seeded random-init weights of the metaseg architecture")
+    elif allow_random if allow_random is not None else allow_random_weights():
+        print(f"[ecseg_b200] WARNING: {path} not found -- running with SEEDED RANDOM-INIT weights (explicit opt-in). "
+              "The network was never trained: label maps and ecDNA counts of this run are synthetic.", file=sys.stderr)
         w = wmod.make_weights(0)
-    return MetasegModel(w, precision)
+        synthetic = True
+    else:
+        raise FileNotFoundError(
+            f"no model checkpoint: neither {path} nor {h5} exists (the reference's load_model raises here too). "
+            "Download metaseg.h5 into models/, or opt in to seeded random-init weights with "
+            "ECSEG_ALLOW_RANDOM_WEIGHTS=1 / `allow_random_weights: true` under `metaseg:` in config.yaml.")
+    return MetasegModel(w, precision, synthetic)
 
 
 def get_imgs(inpath):

@@ -31,7 +31,8 @@ typedef struct ecseg_ctx ecseg_ctx;
 #define ECSEG_E_INVALID (-1) /* bad argument (shape, dtype, null pointer) */
 #define ECSEG_E_CUDA (-2)    /* CUDA runtime / driver error, text in ecseg_last_error */
 #define ECSEG_E_STATE (-3)   /* call order (e.g. forward before load_weights) */
-#define ECSEG_E_RANGE (-4)   /* img_as_ubyte range violation: a probability outside [-1, 1] */
+#define ECSEG_E_RANGE (-4)   /* img_as_ubyte range violation (a probability outside [-1, 1] or NaN, src/utils.py:117), or a
+                                U-Net activation that left the 16-bit operand range (inf / NaN) in a tensor-core mode */
 #define ECSEG_E_DEVICE (-5)  /* a kernel reported a device-side failure (pipeline watchdog) */
 
 /* arithmetic of the U-Net (ecseg_load_weights `precision`) */
@@ -220,6 +221,14 @@ int ecseg_debug_trace(ecseg_ctx* ctx, int64_t* out, int n);
 
 /* Synchronise and read the device-side pipeline watchdog flag (0 = healthy). */
 int ecseg_device_error(ecseg_ctx* ctx, int* code);
+
+/* 16-bit range guard of the tensor-core modes.  Keras computes model.predict_on_batch (src/utils.py:115) in fp32; the
+ * fp16 / bf16 epilogues convert every layer output to 16 bit, and an fp16 overflow would turn into inf, then NaN
+ * logits, then label 0 without a word.  Every epilogue therefore tracks the largest 16-bit pattern it stores, and the
+ * first layer that emits an inf / NaN records its index.  Synchronises; *layer = that index (-1: none); returns
+ * ECSEG_E_RANGE when one fired.  The whole-image calls (ecseg_segment_image_host*, *_files*) report the same condition
+ * from their _wait.  conv1-1, whose input is bounded (0..255), is checked once at ecseg_load_weights instead. */
+int ecseg_activation_overflow(ecseg_ctx* ctx, int* layer);
 
 /* Number of kernels this library launched on behalf of ctx since creation. */
 int64_t ecseg_launch_count(ecseg_ctx* ctx);

@@ -17,6 +17,9 @@ Fixtures (all small, compressed):
   preprocess.npz  meta_preprocess on u8/u16/gray/RGB/bright-background inputs
   segment.npz     utils.meta_segment end to end with a deterministic fake model (tif on disk)
   overlay.npz     meta_overlay's per-image counts (count_cc / count_colocalization / count_HSR)
+  example.npz     BASELINE config 1: utils.meta_segment on input.tif := 255 - example_ecSeg/dapi.jpeg
+                  (the only fixture the reference ships; SURVEY.md finding 0.4) with the fp32 torch-CPU
+                  U-Net oracle standing in for Keras, seed-0 weights (`python oracle/make_golden.py example`)
 """
 from __future__ import annotations
 
@@ -124,12 +127,79 @@ def gen_overlay(it):
     print("overlay.npz:", len(cases), "cases")
 
 
+EXAMPLE_JPEG = "/root/reference/example_ecSeg/dapi.jpeg"
+
+
+def gen_example(it, ut):
+    """BASELINE.json config 1.  example_ecSeg/input.tif is missing from the reference checkout
+    (.MISSING_LARGE_BLOBS); dapi.jpeg is the reference's own dapi/ output for it, i.e. 255 - the
+    pre-processed image (src/utils.py:112), so input.tif := 255 - dapi.jpeg (JPEG-lossy).  The reference's
+    utils.meta_segment (src/utils.py:109-120) runs UNMODIFIED on that file; the model object is the fp32
+    torch-CPU U-Net oracle (seed-0 weights) wrapped to record what predict_on_batch returned, and the raw
+    (pre-meta_inference) label map is rebuilt from those predictions with the reference's own
+    patches2im_overlap + img_as_ubyte + np.argmax (src/utils.py:116-118)."""
+    from skimage import img_as_ubyte          # the harness stub the reference itself imports
+
+    from ecseg_b200 import weights as wmod
+    from oracle.unet_oracle import UNetOracle
+
+    jpg = cv2.imread(EXAMPLE_JPEG, cv2.IMREAD_GRAYSCALE)
+    assert jpg is not None and jpg.shape == (1040, 1392), "example_ecSeg/dapi.jpeg not found / unexpected shape"
+    inp = (255 - jpg).astype(np.uint8)
+
+    class Recorder:
+        def __init__(self, net):
+            self.net, self.tiles, self.preds = net, None, None
+
+        def predict_on_batch(self, x):
+            self.tiles = np.asarray(x)
+            self.preds = self.net.predict_on_batch(self.tiles)
+            return self.preds
+
+    rec = Recorder(UNetOracle(wmod.make_weights(0), batch=5))
+    with tempfile.TemporaryDirectory() as tmp:
+        os.mkdir(os.path.join(tmp, "dapi"))
+        p = os.path.join(tmp, "input.tif")
+        cv2.imwrite(p, inp)
+        final = ut.meta_segment(rec, p)
+        dapi = cv2.imread(os.path.join(tmp, "dapi", "input.tif"), cv2.IMREAD_UNCHANGED)
+    assert rec.tiles.shape == (35, 256, 256, 1) and rec.tiles.dtype == np.uint8
+    _img, _patches, pos = it.im2patches_overlap(it.meta_preprocess(inp.copy())[..., None])
+    canvas = it.patches2im_overlap(list(rec.preds), pos)
+    q = img_as_ubyte(canvas)
+    raw = np.argmax(q, axis=2)
+    again = it.meta_inference(raw.copy())
+    assert np.array_equal(again, final), "rebuilt raw label map does not reproduce meta_segment's result"
+    srt = np.sort(q.astype(np.int16), axis=2)
+    notie = srt[..., 3] != srt[..., 2]
+    z = rec.net.predict_logits(rec.tiles)
+    d = {
+        "input": inp, "dapi": dapi, "pos": np.array(pos, np.int64),
+        "raw": raw.astype(np.uint8),                     # label map at the src/utils.py:118 -> :119 boundary
+        "notie": np.packbits(notie),                     # pixels whose quantised top-2 differ (agreement metric)
+        "final": final.astype(np.uint8),                 # meta_segment's return value
+        "count": np.array(it.count_cc(final == 3), np.int64),
+        # a sparse, frozen view of the oracle's own arithmetic (every 8th pixel of every tile): lets the GPU box
+        # check that ITS torch-CPU build reproduces the oracle that generated this file
+        "logits_sub8": z[:, ::8, ::8, :].astype(np.float32),
+        "logits_absmax": np.array(float(np.abs(z).max())),
+        "hist_raw": np.bincount(raw.ravel(), minlength=4).astype(np.int64),
+        "hist_final": np.bincount(final.ravel().astype(np.int64), minlength=4).astype(np.int64),
+    }
+    np.savez_compressed(os.path.join(OUT, "example.npz"), **d)
+    print("example.npz: 1040x1392, 35 tiles; raw hist", d["hist_raw"], "final hist", d["hist_final"], "count", d["count"],
+          "ties %.3f%%" % (100 * (1 - notie.mean())))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     warnings.simplefilter("ignore")
     it, ut = ref_harness.load_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "overlay":
         gen_overlay(it)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "example":
+        gen_example(it, ut)
         return
     nested = lift_nested(it.meta_inference)
     assert set(nested) >= {"merge_comp", "fill_holes", "size_thresh"}, nested.keys()
@@ -222,6 +292,7 @@ def main():
     print("segment.npz:", len(seg_in), "images")
 
     gen_overlay(it)
+    gen_example(it, ut)
 
 
 if __name__ == "__main__":

@@ -6,7 +6,9 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-COMMON = ["bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-tiles", "1"]
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+COMMON = ["bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0"]
 
 
 def _check(line, n_gpus):
@@ -22,6 +24,15 @@ def _check(line, n_gpus):
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     e = d["e2e"]
     assert e["value"] == d["value"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+    # a MEASURED arm: the timed region is steps x the step time, the stages add up to it, nothing is scaled
+    assert abs(d["timed_region_s"] - d["steps"] * d["ms_per_step"] / 1e3) < 1e-6
+    st = d["cpu_stage_s_per_image"]
+    assert set(st) == {"preprocess_tile", "unet", "stitch_quantise_argmax", "meta_inference", "count_cc"}
+    assert abs(sum(st.values()) - d["ms_per_step"] / 1e3) < 0.05 * d["ms_per_step"] / 1e3
+    assert "extrapolat" in cb["sample"] and "100 tiles" in cb["sample"] and "scaled x" not in cb["sample"]
+    # same `config` as the GPU arm prints (the driver compares the two arms on it)
+    import bench
+    assert d["config"] == bench.workload_config(8, 2, 8)
 
 
 def test_reference_arm_single_process():

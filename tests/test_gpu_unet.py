@@ -11,6 +11,7 @@ pytestmark = pytest.mark.gpu
 
 LOGIT_REL_TOL_FP32 = 1e-3
 LABEL_AGREEMENT = 0.999
+BF16_FLOOR = 0.995
 
 
 @pytest.fixture(scope="module")
@@ -63,8 +64,52 @@ def test_tensor_core_modes(setup, prec):
     rel = np.abs(z - s["z_ref"]).max() / np.abs(s["z_ref"]).max()
     agree, ties = _agreement(probs.cpu().numpy(), s["p_ref"])
     print(f"{prec}: logits max rel err {rel:.3e}, label agreement {agree * 100:.4f}% (ties {ties * 100:.3f}%)")
+    assert eng.activation_overflow() == -1
     assert rel <= (6e-2 if prec == "bf16" else 1e-2), rel
-    assert agree >= (0.99 if prec == "bf16" else LABEL_AGREEMENT), (agree, ties)
+    # fp16 is the throughput dtype and carries the 99.9 % bar.  bf16 (8-bit mantissa) cannot reach it on this network
+    # (SURVEY section 7 probe: 99.87 %, measured here ~99.8 %): it stays selectable for checkpoints whose activations
+    # leave the fp16 range, with a regression floor here and the bar itself recorded as an expected failure below.
+    assert agree >= (BF16_FLOOR if prec == "bf16" else LABEL_AGREEMENT), (agree, ties)
+
+
+@pytest.mark.xfail(reason="bf16 operands (8-bit mantissa) measure ~99.8 % < the 99.9 % label bar; fp16 -- same tcgen05 "
+                          "kind::f16 rate -- is the throughput dtype (DESIGN.md section 2)", strict=False)
+def test_bf16_at_the_label_bar(setup):
+    s = setup
+    eng = s["eng"]
+    eng.load_weights(s["w"], "bf16")
+    agree, _ = _agreement(eng.unet_forward(s["tiles"][..., 0]).cpu().numpy(), s["p_ref"])
+    print(f"bf16 label agreement {agree * 100:.4f}%")
+    assert agree >= LABEL_AGREEMENT, agree
+
+
+def test_fp16_range_guard_fires_on_overflow(setup):
+    """With a real checkpoint nothing bounds the activations; an fp16 overflow in an epilogue conversion would become
+    inf -> NaN logits -> label 0 silently.  Scaled-up weights must raise ECSEG_E_RANGE (ValueError) and name the
+    layer, in the staged and in the whole-image call; bf16 and fp32 run the same weights without complaint; conv1-1
+    (bounded input) is rejected at load time."""
+    import copy
+    s = setup
+    eng = s["eng"]
+    big = copy.copy(s["w"])
+    big["conv1-2/kernel"] = np.asarray(s["w"]["conv1-2/kernel"]) * np.float32(3e4)
+    eng.load_weights(big, "fp16")
+    eng.unet_forward(s["tiles"][..., 0])
+    with pytest.raises(ValueError, match="layer 1 "):
+        eng.activation_overflow()
+    with pytest.raises(ValueError, match="16-bit operand range"):
+        eng.segment_host(s["img"])
+    eng.load_weights(big, "bf16")
+    eng.unet_forward(s["tiles"][..., 0])
+    assert eng.activation_overflow() == -1
+    first = copy.copy(s["w"])
+    first["conv1-1/kernel"] = np.asarray(s["w"]["conv1-1/kernel"]) * np.float32(1e4)
+    with pytest.raises(ValueError, match="conv1-1"):
+        eng.load_weights(first, "fp16")
+    eng.load_weights(first, "bf16")            # bf16 has fp32's exponent range
+    eng.load_weights(s["w"], "fp16")
+    eng.unet_forward(s["tiles"][..., 0])
+    assert eng.activation_overflow() == -1     # the flag does not stick
 
 
 @pytest.mark.parametrize("prec", ["fp32", "fp16"])
