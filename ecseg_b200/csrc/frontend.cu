@@ -30,11 +30,66 @@ __device__ __forceinline__ uint8_t scale_u16(unsigned int v) {
   return (uint8_t)min(max(q, 0), 255);
 }
 
-// Pass 1: channel pick (channel 2 of colour images, image_tools.py:88-89), u16->u8, 256-bin histogram.
+// Otsu threshold as OpenCV's getThreshVal_Otsu_8u computes it (double precision, first maximum), then the
+// reference's polarity test  sum(px > T) > 0.5*H*W  (image_tools.py:91-95), from a 256-bin histogram in SHARED
+// memory.  The recurrences (q1, mu1 carried from bin to bin through a multiply, an add and a divide, each rounded)
+// are order dependent, so bit-identity with the CPU needs the sequential chain: ONE thread walks it, with explicit
+// _rn intrinsics (no FMA contraction).  Everything that is order independent runs on the whole block: the first
+// moment (integers below 2^53: exact in any order) and the count above the threshold.
+__device__ void otsu_from_hist(const unsigned int* sh, int n_px, Counters* cnt) {
+  __shared__ int s_thr;
+  __shared__ unsigned long long s_moment, s_above;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { s_moment = 0ull; s_above = 0ull; }
+  __syncthreads();
+  unsigned long long m = 0;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) m += (unsigned long long)i * sh[i];
+  for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+  if (lane == 0 && m) atomicAdd(&s_moment, m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double scale = __ddiv_rn(1.0, (double)n_px);
+    // sum_i i*hist[i] accumulated in double by OpenCV; every partial sum is an integer < 2^53, so the order is immaterial
+    const double mu = __dmul_rn((double)s_moment, scale);
+    double mu1 = 0.0, q1 = 0.0, max_sigma = 0.0;
+    int max_val = 0;
+    const double eps = 1.1920928955078125e-07;  // FLT_EPSILON
+    for (int i = 0; i < 256; ++i) {
+      const double p_i = __dmul_rn((double)sh[i], scale);
+      mu1 = __dmul_rn(mu1, q1);
+      q1 = __dadd_rn(q1, p_i);
+      const double q2 = __dsub_rn(1.0, q1);
+      if (fmin(q1, q2) < eps || fmax(q1, q2) > 1.0 - eps) continue;
+      mu1 = __ddiv_rn(__dadd_rn(mu1, __dmul_rn((double)i, p_i)), q1);
+      const double mu2 = __ddiv_rn(__dsub_rn(mu, __dmul_rn(q1, mu1)), q2);
+      const double d = __dsub_rn(mu1, mu2);
+      const double sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), d), d);
+      if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
+    }
+    s_thr = max_val;
+  }
+  __syncthreads();
+  const int thr = s_thr;
+  unsigned long long above = 0;
+  for (int i = thr + 1 + threadIdx.x; i < 256; i += blockDim.x) above += sh[i];
+  for (int o = 16; o > 0; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
+  if (lane == 0 && above) atomicAdd(&s_above, above);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cnt->otsu_threshold = thr;
+    cnt->n_above = s_above;
+    cnt->flip = ((double)s_above > (double)n_px * 0.5) ? 1 : 0;
+  }
+}
+
+// Pass 1: channel pick (channel 2 of colour images, image_tools.py:88-89), u16->u8, 256-bin histogram; the LAST
+// block to finish evaluates the Otsu threshold (no separate one-thread launch, no round trip of the histogram
+// through another kernel's global loads).
 template <typename T>
 __global__ void k_pre_convert_hist(const T* __restrict__ img, int n_px, int ch, uint8_t* __restrict__ pre,
                                    Counters* __restrict__ cnt) {
   __shared__ unsigned int sh[256];
+  __shared__ int s_last;
   for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   const int pick = ch > 1 ? 2 : 0;
@@ -47,38 +102,15 @@ __global__ void k_pre_convert_hist(const T* __restrict__ img, int n_px, int ch, 
   __syncthreads();
   for (int i = threadIdx.x; i < 256; i += blockDim.x)
     if (sh[i]) atomicAdd(&cnt->hist[i], sh[i]);
-}
-
-// Otsu threshold as OpenCV's getThreshVal_Otsu_8u computes it (double precision, first maximum),
-// then the reference's polarity test  sum(px > T) > 0.5*H*W  (image_tools.py:91-95).
-// One thread: 256 iterations of scalar fp64, no FMA contraction (explicit _rn intrinsics) so the
-// result is bit-identical to the CPU evaluation order.
-__global__ void k_otsu(Counters* cnt, int n_px) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const double scale = __ddiv_rn(1.0, (double)n_px);
-  double mu = 0.0;
-  for (int i = 0; i < 256; ++i) mu = __dadd_rn(mu, __dmul_rn((double)i, (double)cnt->hist[i]));
-  mu = __dmul_rn(mu, scale);
-  double mu1 = 0.0, q1 = 0.0, max_sigma = 0.0;
-  int max_val = 0;
-  const double eps = 1.1920928955078125e-07;  // FLT_EPSILON
-  for (int i = 0; i < 256; ++i) {
-    double p_i = __dmul_rn((double)cnt->hist[i], scale);
-    mu1 = __dmul_rn(mu1, q1);
-    q1 = __dadd_rn(q1, p_i);
-    double q2 = __dsub_rn(1.0, q1);
-    if (fmin(q1, q2) < eps || fmax(q1, q2) > 1.0 - eps) continue;
-    mu1 = __ddiv_rn(__dadd_rn(mu1, __dmul_rn((double)i, p_i)), q1);
-    double mu2 = __ddiv_rn(__dsub_rn(mu, __dmul_rn(q1, mu1)), q2);
-    double d = __dsub_rn(mu1, mu2);
-    double sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), d), d);
-    if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
-  }
-  unsigned long long above = 0;
-  for (int i = max_val + 1; i < 256; ++i) above += cnt->hist[i];
-  cnt->otsu_threshold = max_val;
-  cnt->n_above = above;
-  cnt->flip = ((double)above > (double)n_px * 0.5) ? 1 : 0;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&cnt->pre_ticket, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = __ldcg(&cnt->hist[i]);
+  __syncthreads();
+  otsu_from_hist(sh, n_px, cnt);
 }
 
 // Pass 2: apply the polarity flip (~img) and emit the dapi/ artefact (255 - pre, utils.py:112).
@@ -106,8 +138,6 @@ int fe_preprocess(ecseg_ctx* ctx, const void* d_img, int h, int w, int ch, int b
     k_pre_convert_hist<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t*)d_img, n_px, ch, d_pre, ctx->counters);
   else
     k_pre_convert_hist<uint16_t><<<blocks, 256, 0, st>>>((const uint16_t*)d_img, n_px, ch, d_pre, ctx->counters);
-  ECSEG_CHECK_LAUNCH();
-  k_otsu<<<1, 32, 0, st>>>(ctx->counters, n_px);
   ECSEG_CHECK_LAUNCH();
   k_pre_apply<<<blocks, 256, 0, st>>>(d_pre, d_dapi, n_px, ctx->counters);
   ECSEG_CHECK_LAUNCH();
