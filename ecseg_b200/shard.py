@@ -121,10 +121,14 @@ def main(argv=None) -> int:
         np.save(out, I)
         return model.last_count
 
+    stats = {"rank": rank, "images": 0, "wall_s": 0.0}
+
     def process_batch(mine: list) -> list:
         """This rank's share: *.tif through the overlapped pipeline on this GPU, anything else one by one."""
+        import time
         tifs = [p for p in mine if p.lower().endswith('.tif')]
         counts = {}
+        t0 = time.perf_counter()
         if tifs and not os.environ.get("ECSEG_SERIAL"):
             from . import tiffio
             from .pipeline import FilesPipeline
@@ -137,10 +141,21 @@ def main(argv=None) -> int:
                 counts.update(dict(pipe.run(tifs)))
             finally:
                 pipe.close()
-        return [counts[p] if p in counts else process_one(p) for p in mine]
+        out = [counts[p] if p in counts else process_one(p) for p in mine]
+        stats["images"], stats["wall_s"] = len(mine), time.perf_counter() - t0
+        return out
 
+    if world > 1:
+        dist.barrier()          # every rank has its model: the shares start together (the job's rate is images / slowest share)
     rows = run_sharded(paths, process_one, rank, world, lambda r: dist_gather(r, rank, world), process_batch)
+    all_stats = dist_gather([stats], rank, world)
     if rows is not None:
+        import json
+        per_rank = [s[0] for s in all_stats]
+        wall = max(s["wall_s"] for s in per_rank)
+        print("[ecseg_b200.shard] " + json.dumps({"world": world, "images": len(rows), "slowest_share_s": wall,
+                                                   "images_per_s": len(rows) / wall if wall > 0 else None,
+                                                   "per_rank": per_rank, "host_cores": os.cpu_count()}))
         csv_path = os.path.join(inpath, 'ec_quantification.csv')
         print("Saving ec quantification to", csv_path)
         write_csv(csv_path, rows)
