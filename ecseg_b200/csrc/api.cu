@@ -86,6 +86,7 @@ void ecseg_ctx_destroy(ecseg_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   unet_destroy(ctx);
+  pp_free_graphs(ctx);
   art_free_workspace(ctx);
   if (ctx->trace) cudaFree(ctx->trace);
   void* ptrs[] = {ctx->L, ctx->area, ctx->sum_y, ctx->sum_x, ctx->flag, ctx->tmp_a, ctx->tmp_b, ctx->chrom_cy,

@@ -121,6 +121,14 @@ struct ecseg_ctx {
   size_t png_zcap = 0;
   struct FilesJob { uint8_t* h_png = nullptr; size_t png_cap = 0; int h = 0, w = 0; cudaStream_t st = nullptr; } job;
 
+  // post-processing as a replayed CUDA graph (postproc.cu): one instantiated graph per distinct argument set
+  struct PpGraph {
+    uint8_t* cls; int h, w, flags; int32_t* d_n; int64_t* d_px; int parity_in, parity_out; int n_launches;
+    cudaGraphExec_t exec; unsigned long long stamp;
+  };
+  std::vector<PpGraph> pp_graphs;
+  unsigned long long pp_stamp = 0;
+
   long long* trace = nullptr;           // pipeline trace buffer (ecseg_debug_trace), allocated on first use
   ecseg::UNet* net = nullptr;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -165,6 +173,7 @@ int fe_stitch_argmax(ecseg_ctx* ctx, const float* d_probs, int h, int w, uint8_t
 
 int pp_postprocess(ecseg_ctx* ctx, uint8_t* d_labels, int h, int w, int flags, int32_t* d_n_ec,
                    int64_t* d_ec_px, cudaStream_t st);
+void pp_free_graphs(ecseg_ctx* ctx);
 int pp_count_cc(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w, int32_t* d_n, int64_t* d_px,
                 cudaStream_t st);
 int pp_fill_holes(ecseg_ctx* ctx, uint8_t* d_labels, int h, int w, int class_id, cudaStream_t st);

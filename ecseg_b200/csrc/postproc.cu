@@ -17,6 +17,8 @@
 // All kernels are HBM-bound byte/int kernels: one thread per pixel, a warp covers 32 consecutive
 // pixels of one image row so that horizontal runs are resolved with one ballot (no memory
 // traffic), and only run heads issue union operations.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ecseg {
@@ -924,13 +926,8 @@ int pp_label(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w, int conn, int3
 // ------------------------------------------------------------------------------------------------
 // meta_inference in execution order  (image_tools.py:61-83)  + count_cc(I == 3)
 // ------------------------------------------------------------------------------------------------
-int pp_postprocess(ecseg_ctx* ctx, uint8_t* cls, int h, int w, int flags, int32_t* d_n_ec, int64_t* d_ec_px,
-                   cudaStream_t st) {
-  if (!cls || h < 1 || w < 1 || (size_t)h * w > ctx->max_px) {
-    ctx->err = "ecseg_postprocess: image larger than the context's max_h x max_w";
-    return ECSEG_E_INVALID;
-  }
-  if (reinterpret_cast<uintptr_t>(cls) & 7) { ctx->err = "ecseg_postprocess: label map must be 8-byte aligned"; return ECSEG_E_INVALID; }
+static int pp_postprocess_launches(ecseg_ctx* ctx, uint8_t* cls, int h, int w, int flags, int32_t* d_n_ec, int64_t* d_ec_px,
+                                  cudaStream_t st) {
   uint8_t* t = ctx->tmp_a;
   ECSEG_TRY(pp_fill_holes(ctx, cls, h, w, 1, st));                       // :61
   ECSEG_TRY(pp_fill_holes(ctx, cls, h, w, 2, st));                       // :61
@@ -945,6 +942,64 @@ int pp_postprocess(ecseg_ctx* ctx, uint8_t* cls, int h, int w, int flags, int32_
   k_ec_dilate<<<row4_grid(h, w), 128, 0, st>>>(t, cls, h, w);       // :83   t -> cls
   ECSEG_CHECK_LAUNCH();
   if (d_n_ec || d_ec_px) ECSEG_TRY(count_mode(ctx, cls, h, w, KEY_EQ, 3, d_n_ec, d_ec_px, st));  // metaseg.py:46
+  return ECSEG_OK;
+}
+
+void pp_free_graphs(ecseg_ctx* ctx) {
+  for (auto& g : ctx->pp_graphs) cudaGraphExecDestroy(g.exec);
+  ctx->pp_graphs.clear();
+}
+
+// The 24 launches of one label map are small (4-47 us) and strictly dependent: issued one by one, the stage is bound by
+// launch latency, not by HBM.  The sequence depends only on the arguments (pointers, shape, flags, labelling parity),
+// never on the data, so it is captured once per distinct argument set into a CUDA graph and replayed: one graph
+// launch per map, the dependent kernels chained on the device.  ECSEG_PP_NO_GRAPH=1 (or the legacy default stream,
+// which cannot be captured) issues the launches directly.
+int pp_postprocess(ecseg_ctx* ctx, uint8_t* cls, int h, int w, int flags, int32_t* d_n_ec, int64_t* d_ec_px,
+                   cudaStream_t st) {
+  if (!cls || h < 1 || w < 1 || (size_t)h * w > ctx->max_px) {
+    ctx->err = "ecseg_postprocess: image larger than the context's max_h x max_w";
+    return ECSEG_E_INVALID;
+  }
+  if (reinterpret_cast<uintptr_t>(cls) & 7) { ctx->err = "ecseg_postprocess: label map must be 8-byte aligned"; return ECSEG_E_INVALID; }
+  if ((size_t)cdiv(w, kCclTile) * cdiv(h, kCclTile) > ctx->max_ccl_tiles) {
+    ctx->err = "labelling: image aspect ratio needs more 32x32 tiles than the context was sized for";
+    return ECSEG_E_INVALID;
+  }
+  static const bool no_graph = getenv("ECSEG_PP_NO_GRAPH") != nullptr;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (no_graph || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread ||
+      cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
+    return pp_postprocess_launches(ctx, cls, h, w, flags, d_n_ec, d_ec_px, st);
+  const int parity = ctx->ccl_parity;
+  for (auto& g : ctx->pp_graphs) {
+    if (g.cls == cls && g.h == h && g.w == w && g.flags == flags && g.d_n == d_n_ec && g.d_px == d_ec_px && g.parity_in == parity) {
+      ECSEG_CUDA(cudaGraphLaunch(g.exec, st));
+      g.stamp = ++ctx->pp_stamp;
+      ctx->ccl_parity = g.parity_out;
+      ctx->launches += g.n_launches;
+      return ECSEG_OK;
+    }
+  }
+  const int64_t launches0 = ctx->launches;
+  ECSEG_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  const int rc = pp_postprocess_launches(ctx, cls, h, w, flags, d_n_ec, d_ec_px, st);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rc != ECSEG_OK) { if (graph) cudaGraphDestroy(graph); ctx->ccl_parity = parity; return rc; }
+  if (ce != cudaSuccess || !graph) { ctx->err = std::string("post-processing graph capture failed: ") + cudaGetErrorString(ce); return ECSEG_E_CUDA; }
+  ecseg_ctx::PpGraph g = {cls, h, w, flags, d_n_ec, d_ec_px, parity, ctx->ccl_parity, (int)(ctx->launches - launches0), nullptr, ++ctx->pp_stamp};
+  const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) { ctx->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie); return ECSEG_E_CUDA; }
+  if (ctx->pp_graphs.size() >= 32) {      // bounded cache: drop the least recently used argument set
+    size_t old = 0;
+    for (size_t i = 1; i < ctx->pp_graphs.size(); ++i) if (ctx->pp_graphs[i].stamp < ctx->pp_graphs[old].stamp) old = i;
+    cudaGraphExecDestroy(ctx->pp_graphs[old].exec);
+    ctx->pp_graphs.erase(ctx->pp_graphs.begin() + old);
+  }
+  ctx->pp_graphs.push_back(g);
+  ECSEG_CUDA(cudaGraphLaunch(g.exec, st));
   return ECSEG_OK;
 }
 

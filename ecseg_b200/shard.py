@@ -121,7 +121,7 @@ def main(argv=None) -> int:
         np.save(out, I)
         return model.last_count
 
-    stats = {"rank": rank, "images": 0, "wall_s": 0.0}
+    stats = {"rank": rank, "images": 0, "wall_s": 0.0, "setup_s": 0.0}
 
     def process_batch(mine: list) -> list:
         """This rank's share: *.tif through the overlapped pipeline on this GPU, anything else one by one."""
@@ -137,7 +137,9 @@ def main(argv=None) -> int:
                                  max(max(s[1] for s in shapes), 256), device=local, n_ctx=int(var.get('contexts', 2)),
                                  n_readers=int(var.get('readers', 4)), n_writers=int(var.get('writers', 6)),
                                  max_bytes_per_px=max(s[2] * s[3] for s in shapes))
+            stats["setup_s"] = time.perf_counter() - t0      # contexts, weight upload, pinned slots
             try:
+                t0 = time.perf_counter()
                 counts.update(dict(pipe.run(tifs)))
             finally:
                 pipe.close()
@@ -155,6 +157,8 @@ def main(argv=None) -> int:
         wall = max(s["wall_s"] for s in per_rank)
         print("[ecseg_b200.shard] " + json.dumps({"world": world, "images": len(rows), "slowest_share_s": wall,
                                                    "images_per_s": len(rows) / wall if wall > 0 else None,
+                                                   "note": "wall_s = this rank's share through the pipeline (decode, GPU, file "
+                                                           "writes); setup_s = contexts + weight upload before it",
                                                    "per_rank": per_rank, "host_cores": os.cpu_count()}))
         csv_path = os.path.join(inpath, 'ec_quantification.csv')
         print("Saving ec quantification to", csv_path)

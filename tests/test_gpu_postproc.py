@@ -99,3 +99,42 @@ def test_postprocess_idempotent_count(eng):
     out, n, px = eng.postprocess(m)
     assert eng.count_cc(out == 3) == (n, px)
     assert int((out == 3).sum().item()) == px
+
+
+def test_graph_replay_same_buffers_different_maps(eng, golden):
+    """On a non-default stream ecseg_postprocess captures its launch sequence once per argument set and replays it
+    (postproc.cu pp_postprocess).  Same device buffers, changing contents and both labelling parities: every replay
+    must equal the oracle bit for bit, and count as 24 launches."""
+    import torch
+    from ctypes import c_void_p
+    from ecseg_b200 import synth
+    mo = _oracle()
+    dev = eng.device
+    s = torch.cuda.Stream(device=dev)
+    h, w = 300, 420
+    buf = torch.empty((h, w), dtype=torch.uint8, device=dev)
+    n = torch.zeros(1, dtype=torch.int32, device=dev)
+    px = torch.zeros(1, dtype=torch.int64, device=dev)
+    per_call = []
+    for seed in range(7):
+        m = synth.synth_label_map(40 + seed, h, w) if seed % 2 else synth.synth_noise_label_map(40 + seed, h, w, block=2)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = mo.meta_inference(m.astype(np.int64).copy())
+        src = torch.from_numpy(m).to(dev)
+        l0 = eng.launch_count()
+        with torch.cuda.stream(s):
+            buf.copy_(src, non_blocking=True)
+            eng._chk(eng.lib.ecseg_postprocess(eng.ctx, buf.data_ptr(), h, w, 0, n.data_ptr(), px.data_ptr(), c_void_p(s.cuda_stream)))
+        s.synchronize()
+        per_call.append(eng.launch_count() - l0)
+        assert np.array_equal(buf.cpu().numpy(), want), seed
+        assert (int(n.item()), int(px.item())) == mo.count_cc(want == 3), seed
+    assert len(set(per_call)) == 1 and per_call[0] >= 20, per_call       # replays account for the same launches
+    # golden cases through the graph path too (fresh buffers: captured, launched once, evicted from the bounded cache)
+    g = golden("postproc")
+    with torch.cuda.stream(s):
+        for i in range(int(g["n_cases"])):
+            out, cnt, cpx = eng.postprocess(g[f"in_{i}"], faithful_merge=bool(i % 2))
+            assert np.array_equal(out.cpu().numpy(), g[f"out_{i}"]), i
+            assert (cnt, cpx) == tuple(int(v) for v in g[f"cnt_{i}"]), i
