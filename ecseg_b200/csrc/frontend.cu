@@ -32,13 +32,18 @@ __device__ __forceinline__ uint8_t scale_u16(unsigned int v) {
 
 // Otsu threshold as OpenCV's getThreshVal_Otsu_8u computes it (double precision, first maximum), then the
 // reference's polarity test  sum(px > T) > 0.5*H*W  (image_tools.py:91-95), from a 256-bin histogram in SHARED
-// memory.  The recurrences (q1, mu1 carried from bin to bin through a multiply, an add and a divide, each rounded)
-// are order dependent, so bit-identity with the CPU needs the sequential chain: ONE thread walks it, with explicit
-// _rn intrinsics (no FMA contraction).  Everything that is order independent runs on the whole block: the first
-// moment (integers below 2^53: exact in any order) and the count above the threshold.
+// memory, bit-identical to the CPU evaluation (explicit _rn intrinsics, no FMA contraction).
+// Only the (q1, mu1) recurrence is order dependent -- each bin's values come from the previous bin's through a
+// multiply, an add and a divide, each rounded -- so ONE thread walks that chain (one divide per bin) and leaves
+// (q1_i, mu1_i) in shared memory; the between-class variance of every bin (second divide, three multiplies) is then
+// evaluated by 256 threads at once from exactly the operands the sequential code would have used, and the first
+// maximum is found by a reduction that prefers the lower bin on ties (`sigma > max_sigma` is strict in OpenCV).
+// The first moment (integers below 2^53: exact in any order) and the count above the threshold are block reductions.
 __device__ void otsu_from_hist(const unsigned int* sh, int n_px, Counters* cnt) {
   __shared__ int s_thr;
   __shared__ unsigned long long s_moment, s_above;
+  __shared__ double s_q1[256], s_mu1[256], s_sig[256];
+  __shared__ double s_mu;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) { s_moment = 0ull; s_above = 0ull; }
   __syncthreads();
@@ -47,26 +52,51 @@ __device__ void otsu_from_hist(const unsigned int* sh, int n_px, Counters* cnt) 
   for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
   if (lane == 0 && m) atomicAdd(&s_moment, m);
   __syncthreads();
+  const double scale = __ddiv_rn(1.0, (double)n_px);
+  const double eps = 1.1920928955078125e-07;  // FLT_EPSILON
   if (threadIdx.x == 0) {
-    const double scale = __ddiv_rn(1.0, (double)n_px);
     // sum_i i*hist[i] accumulated in double by OpenCV; every partial sum is an integer < 2^53, so the order is immaterial
-    const double mu = __dmul_rn((double)s_moment, scale);
-    double mu1 = 0.0, q1 = 0.0, max_sigma = 0.0;
-    int max_val = 0;
-    const double eps = 1.1920928955078125e-07;  // FLT_EPSILON
+    s_mu = __dmul_rn((double)s_moment, scale);
+    double mu1 = 0.0, q1 = 0.0;
     for (int i = 0; i < 256; ++i) {
       const double p_i = __dmul_rn((double)sh[i], scale);
       mu1 = __dmul_rn(mu1, q1);
       q1 = __dadd_rn(q1, p_i);
       const double q2 = __dsub_rn(1.0, q1);
-      if (fmin(q1, q2) < eps || fmax(q1, q2) > 1.0 - eps) continue;
+      if (fmin(q1, q2) < eps || fmax(q1, q2) > 1.0 - eps) { s_q1[i] = -1.0; continue; }     // bin skipped (`continue`)
       mu1 = __ddiv_rn(__dadd_rn(mu1, __dmul_rn((double)i, p_i)), q1);
-      const double mu2 = __ddiv_rn(__dsub_rn(mu, __dmul_rn(q1, mu1)), q2);
-      const double d = __dsub_rn(mu1, mu2);
-      const double sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), d), d);
-      if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
+      s_q1[i] = q1;
+      s_mu1[i] = mu1;
     }
-    s_thr = max_val;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    double sigma = -1.0;                      // skipped bins never win (max_sigma starts at 0, comparison is strict)
+    const double q1 = s_q1[i];
+    if (q1 >= 0.0) {
+      const double q2 = __dsub_rn(1.0, q1), mu1 = s_mu1[i];
+      const double mu2 = __ddiv_rn(__dsub_rn(s_mu, __dmul_rn(q1, mu1)), q2);
+      const double d = __dsub_rn(mu1, mu2);
+      sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), d), d);
+    }
+    s_sig[i] = sigma;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    // first maximum over the 256 bins: each lane scans its 8 consecutive bins in order, then lanes combine preferring
+    // the lower bin on equal sigma; a maximum of 0 (or no valid bin) leaves the threshold at 0 like the scalar loop
+    double best = 0.0;
+    int arg = 0;
+    for (int k = 0; k < 8; ++k) {
+      const int i = lane * 8 + k;
+      if (s_sig[i] > best) { best = s_sig[i]; arg = i; }
+    }
+    for (int o = 1; o < 32; o <<= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ob > best || (ob == best && ob > 0.0 && oa < arg)) { best = ob; arg = oa; }
+    }
+    if (lane == 0) s_thr = best > 0.0 ? arg : 0;
   }
   __syncthreads();
   const int thr = s_thr;

@@ -101,3 +101,37 @@ def test_meta_overlay_cli(tmp_path):
     assert lines[1] == want
     red = cv2.imread(str(data / "red" / "x.tif.png"), cv2.IMREAD_UNCHANGED)
     assert np.array_equal(red, 255 - I[..., 0])
+
+
+def test_config5_chain_metaseg_then_meta_overlay(tmp_path):
+    """BASELINE config 5 as the user runs it: `make metaseg` then `make meta_overlay` over the same folder of synthetic
+    RGB DAPI + green / red FISH images (DAPI in the blue channel, src/image_tools.py:88-89).  metaseg's
+    labels/<stem>.npy feeds meta_overlay through read_seg (src/utils.py:125-132); all nine count columns of
+    fish_quantification.csv must equal the oracle's overlay_counts on the label map metaseg wrote."""
+    from ecseg_b200 import synth
+    from oracle import metaseg_oracle as mo
+    data = tmp_path / "data"
+    data.mkdir()
+    imgs = {"f0.tif": synth.synth_fish(21, 462, 470), "f1.tif": synth.synth_fish(22, 300, 330, dtype="u16")}
+    for name, I in imgs.items():
+        cv2.imwrite(str(data / name), I[..., ::-1])
+    (tmp_path / "config.yaml").write_text(f"metaseg:\n  inpath: {data}\nmeta_overlay:\n  inpath: {data}\n  color_sensitivity: 85\n")
+    env = dict(os.environ, PYTHONPATH=ROOT, ECSEG_ALLOW_RANDOM_WEIGHTS="1")
+    for script in ("metaseg.py", "meta_overlay.py"):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "src", script)], cwd=str(tmp_path), env=env, capture_output=True,
+                           text=True, timeout=900)
+        assert r.returncode == 0, (script, r.stderr[-2000:])
+    lines = (data / "fish_quantification.csv").read_text().strip().splitlines()
+    rows = {l.split(",", 1)[0]: l for l in lines[1:]}
+    assert set(rows) == set(imgs)
+    cc = lambda t: f'"({t[0]}, {t[1] if t[1] else 0.0})"'
+    ec_csv = dict(l.rsplit(",", 1) for l in (data / "ec_quantification.csv").read_text().strip().splitlines()[1:])
+    for name, I in imgs.items():
+        seg = np.load(data / "labels" / (name[:-4] + ".npy"))
+        assert seg.dtype == np.int64 and seg.shape == I.shape[:2]
+        o = mo.overlay_counts(I, seg.astype(np.uint8), 85)
+        want = ",".join([name, cc(o["num_ecDNA"]), cc(o["num_FISH"]), cc(o["num_FISH2"]), str(o["num_ecDNA_FISH"]),
+                         str(o["num_ecDNA_FISH2"]), str(o["num_FISH_FISH2"]), str(o["num_ecDNA_FISH_FISH2"]),
+                         str(o["num_HSR2"]), str(o["num_HSR"])])
+        assert rows[name] == want, name
+        assert int(ec_csv[name]) == o["num_ecDNA"][0], name        # the two CSVs agree on the ecDNA count (metaseg.py:46)
