@@ -31,6 +31,13 @@ def main():
     ap.add_argument("--port", type=int, default=29611)
     args = ap.parse_args()
     from ecseg_b200 import synth
+    base = args.dir if os.path.isdir(args.dir) else tempfile.gettempdir()
+    per_image = 4 * 2048 * 2048 // 4 + 37948992 + (1 << 20)      # input tif + the three artefacts
+    free = shutil.disk_usage(base).free
+    if free < args.images * per_image * 1.3 + (8 << 30):
+        fit = max(8, int((free - (8 << 30)) / (per_image * 1.3)))
+        print(f"[config3] {base} has {free >> 30} GiB free: {args.images} images do not fit, using {fit}", file=sys.stderr)
+        args.images = fit
     work = tempfile.mkdtemp(prefix="ecseg_cfg3_", dir=args.dir if os.path.isdir(args.dir) else None)
     data = os.path.join(work, "data")
     os.mkdir(data)
