@@ -20,6 +20,8 @@ Fixtures (all small, compressed):
   example.npz     BASELINE config 1: utils.meta_segment on input.tif := 255 - example_ecSeg/dapi.jpeg
                   (the only fixture the reference ships; SURVEY.md finding 0.4) with the fp32 torch-CPU
                   U-Net oracle standing in for Keras, seed-0 weights (`python oracle/make_golden.py example`)
+  config4.npz     BASELINE config 4: reference meta_inference + count_cc on 64 synthetic 2048x2048 label maps
+                  (count tuple, class histogram, SHA-256 of the final map) (`python oracle/make_golden.py config4`)
 """
 from __future__ import annotations
 
@@ -127,6 +129,24 @@ def gen_overlay(it):
     print("overlay.npz:", len(cases), "cases")
 
 
+def gen_config4(it, n_maps=64):
+    """BASELINE config 4 at full size: the reference's meta_inference + count_cc (src/image_tools.py:15-84,114-119) on
+    the first `n_maps` synthetic 2048x2048 label maps the bench cycles (ecseg_b200.synth.synth_label_map, seeds
+    0..n_maps-1).  Frozen per map: the count_cc tuple, the class histogram and a SHA-256 of the final uint8 map."""
+    d = {"cnt": np.zeros((n_maps, 2), np.int64), "hist": np.zeros((n_maps, 4), np.int64), "sha": np.zeros((n_maps, 32), np.uint8)}
+    for s in range(n_maps):
+        m = synth.synth_label_map(s, 2048, 2048)
+        r = it.meta_inference(m.astype(np.int64).copy())
+        n, px = it.count_cc(r == 3)
+        d["cnt"][s] = (int(n), int(px))
+        d["hist"][s] = np.bincount(r.ravel(), minlength=4)
+        d["sha"][s] = np.frombuffer(hashlib.sha256(r.astype(np.uint8).tobytes()).digest(), np.uint8)
+        if s % 8 == 0:
+            print("config4 map", s, d["cnt"][s], flush=True)
+    np.savez_compressed(os.path.join(OUT, "config4.npz"), **d)
+    print("config4.npz:", n_maps, "maps")
+
+
 EXAMPLE_JPEG = "/root/reference/example_ecSeg/dapi.jpeg"
 
 
@@ -200,6 +220,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "example":
         gen_example(it, ut)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "config4":
+        gen_config4(it)
         return
     nested = lift_nested(it.meta_inference)
     assert set(nested) >= {"merge_comp", "fill_holes", "size_thresh"}, nested.keys()
@@ -293,6 +316,7 @@ def main():
 
     gen_overlay(it)
     gen_example(it, ut)
+    gen_config4(it)
 
 
 if __name__ == "__main__":

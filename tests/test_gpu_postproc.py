@@ -138,3 +138,23 @@ def test_graph_replay_same_buffers_different_maps(eng, golden):
             out, cnt, cpx = eng.postprocess(g[f"in_{i}"], faithful_merge=bool(i % 2))
             assert np.array_equal(out.cpu().numpy(), g[f"out_{i}"]), i
             assert (cnt, cpx) == tuple(int(v) for v in g[f"cnt_{i}"]), i
+
+
+def test_config4_maps_vs_reference_run(eng, golden):
+    """BASELINE config 4 on the maps bench.py cycles: the 64 synthetic 2048x2048 label maps (seeds 0..63) against what
+    the reference's own meta_inference + count_cc returned for them (tests/golden/config4.npz, frozen by
+    oracle/make_golden.py gen_config4): count tuple, class histogram and SHA-256 of the final map, all 64 bit-exact."""
+    import hashlib
+    import torch
+    from ecseg_b200 import synth
+    g = golden("config4")
+    n_maps = len(g["cnt"])
+    assert n_maps >= 64
+    s = torch.cuda.Stream(device=eng.device)
+    with torch.cuda.stream(s):          # non-default stream: the graph-replay path the bench uses
+        for seed in range(n_maps):
+            out, n, px = eng.postprocess(synth.synth_label_map(seed, 2048, 2048))
+            o = out.cpu().numpy()
+            assert (n, px) == tuple(int(v) for v in g["cnt"][seed]), seed
+            assert np.array_equal(np.bincount(o.ravel(), minlength=4), g["hist"][seed]), seed
+            assert hashlib.sha256(o.tobytes()).digest() == g["sha"][seed].tobytes(), seed

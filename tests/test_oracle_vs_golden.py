@@ -145,3 +145,16 @@ def test_meta_overlay_counts(golden):
         res = mo.overlay_counts(g[f"img_{i}"], g[f"seg_{i}"], int(g[f"sens_{i}"]))
         assert _flat_overlay(res) == [int(v) for v in g[f"out_{i}"]], i
     assert mo.overlay_counts(g["img_0"][..., 0], g["seg_0"], 85) is None      # non-RGB images are skipped
+
+
+def test_config4_full_size_maps(golden):
+    """The oracle on full-size config-4 maps against the frozen reference run (a sample: ~1.5 s of CPU per map)."""
+    from ecseg_b200 import synth
+    g = golden("config4")
+    for seed in (0, 17, 63):
+        m = synth.synth_label_map(seed, 2048, 2048).astype(np.int64)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out = mo.meta_inference(m)
+        assert mo.count_cc(out == 3) == tuple(int(v) for v in g["cnt"][seed]), seed
+        assert hashlib.sha256(out.astype(np.uint8).tobytes()).digest() == g["sha"][seed].tobytes(), seed
