@@ -2,7 +2,9 @@
 // reference-facing Python shim binds.  No exceptions cross this boundary.
 #include <algorithm>
 #include <cstddef>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "artifacts_host.h"
@@ -38,6 +40,31 @@ static int overflow_error(ecseg_ctx* ctx, int layer1) {
   ctx->err = "U-Net layer " + std::to_string(layer1 - 1) + " produced values outside the 16-bit operand range (inf / NaN after the "
              "fp16 conversion): load the weights with precision bf16 or fp32";
   return ECSEG_E_RANGE;
+}
+
+// One U-Net forward at a time per GPU, across the contexts of a process.  Several contexts on their own streams exist
+// to overlap one image's copies / pre- / post-processing with another image's U-Net -- not to interleave two U-Nets:
+// every conv kernel is a persistent grid over all SMs, so two forwards can only alternate kernel by kernel, and that
+// alternation would push a whole image's worth of another context's activations through the L2 between a sub-batch's
+// producer and consumer (unet_forward's level-0 chain).  With sub-batching on (ECSEG_L0_SUBBATCH, opt-in) each forward
+// therefore waits for the event the previous forward on the device recorded, whichever context issued it
+// (ECSEG_UNET_INTERLEAVE=1 turns that ordering off again).  Without sub-batching the forwards interleave as before:
+// same-box A/B 116.6 (ordered) vs 117.4 (interleaved) images/s, profiles/r02_exp_l0_subbatch.txt.
+static int unet_turnstile(ecseg_ctx* ctx, cudaStream_t st, bool enter) {
+  static std::mutex mu;
+  static cudaEvent_t ev[64] = {};
+  static const bool on = getenv("ECSEG_L0_SUBBATCH") != nullptr && atoi(getenv("ECSEG_L0_SUBBATCH")) > 0 &&
+                         getenv("ECSEG_UNET_INTERLEAVE") == nullptr;
+  if (!on || ctx->device < 0 || ctx->device >= 64) return ECSEG_OK;
+  std::lock_guard<std::mutex> lock(mu);
+  cudaEvent_t& e = ev[ctx->device];
+  if (enter) {
+    if (e) ECSEG_CUDA(cudaStreamWaitEvent(st, e, 0));
+  } else {
+    if (!e) ECSEG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ECSEG_CUDA(cudaEventRecord(e, st));
+  }
+  return ECSEG_OK;
 }
 
 extern "C" {
@@ -227,7 +254,9 @@ int ecseg_segment_image(ecseg_ctx* ctx, const void* d_img, int h, int w, int ch,
   ECSEG_TRY(fe_preprocess(ctx, d_img, h, w, ch, bytes_per_sample, ctx->pre, d_dapi, st));
   ECSEG_CUDA(cudaEventRecord(ctx->ev[1], st));
   // tiles are gathered inside conv1-1, the stitch is fused into the head's epilogue
+  ECSEG_TRY(unet_turnstile(ctx, st, true));
   ECSEG_TRY(unet_forward(ctx, nullptr, ctx->pre, &g, g.n(), nullptr, nullptr, d_labels, st));
+  ECSEG_TRY(unet_turnstile(ctx, st, false));
   ECSEG_CUDA(cudaEventRecord(ctx->ev[2], st));
   ECSEG_CUDA(cudaEventRecord(ctx->ev[3], st));
   ECSEG_TRY(pp_postprocess(ctx, d_labels, h, w, flags, d_n_ec, d_ec_px, st));

@@ -59,7 +59,8 @@ int conv_tc_launch(ecseg_ctx* ctx, ConvTcParams& p, int n_tile, int cluster, cud
 struct HeadTcParams {
   CUtensorMap tm_a;  // conv1-4 output, 4-D {64, 256, 256, N} 16-bit, box {64, 18, 18, 1}, SWIZZLE_128B
   CUtensorMap tm_b;  // head weights, 2-D {64, 48} 16-bit: row = tap*4 + class (rows 36..47 zero), box {64, 48}
-  int n_img;
+  int n_img;         // tiles of this launch (tm_a / probs / logits start at the launch's first tile)
+  int tile0;         // index of that first tile in the image's tile grid (stitch ownership)
   int is_bf16;
   float* probs;      // [n,256,256,4] nullable
   float* logits;     // [n,256,256,4] nullable

@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_head_tc(const __grid_constant__
       tc_fence_before();
       mbar_arrive(tmem_empty(g));             // accumulator drained: the MMAs of this group's next block may start
       // the tile's position in the grid, once per block (runtime divisions stay out of the per-pixel code)
-      const int tci = p.labels ? img / p.grid.nr : 0, tri = img - tci * p.grid.nr;
+      const int gimg = img + p.tile0;     // tile index in the image's grid (this launch may be a sub-batch)
+      const int tci = p.labels ? gimg / p.grid.nr : 0, tri = gimg - tci * p.grid.nr;
       const int sy = p.labels ? p.grid.start_r(tri) + y0 : 0, sx = p.labels ? p.grid.start_c(tci) + x0 : 0;
       named_bar_sync(1 + g, 128);
 #pragma unroll

@@ -69,6 +69,7 @@ struct UNet {
   int fuse_first = 1;
   const uint8_t* in_tiles = nullptr;  // inputs of the forward in flight (read by the fused first layer)
   const uint8_t* in_pre = nullptr;
+  int l0_subbatch = 0;                // tiles per sub-batch of the level-0 decoder chain (0 = whole batch; ECSEG_L0_SUBBATCH)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -359,6 +360,7 @@ int unet_create(ecseg_ctx* ctx) {
   if (const char* e = getenv("ECSEG_TC_CLUSTER")) { const int v = atoi(e); if (v >= 1 && v <= 3) ctx->net->tc_cluster = v; }
   if (const char* e = getenv("ECSEG_TC_NTILE_MAX")) ctx->net->tc_ntile_max = atoi(e);
   if (const char* e = getenv("ECSEG_NO_FUSE_FIRST")) ctx->net->fuse_first = atoi(e) ? 0 : 1;
+  if (const char* e = getenv("ECSEG_L0_SUBBATCH")) { const int v = atoi(e); if (v >= 0 && v <= 4096) ctx->net->l0_subbatch = v; }
   return ECSEG_OK;
 }
 
@@ -559,21 +561,27 @@ static int run_layer_fp32(ecseg_ctx* ctx, int li, int n, float* d_probs, float* 
   return ECSEG_OK;
 }
 
+// Layer `li` over tiles [tile0, tile0 + n) of the batch in the activation buffers (tile0 > 0: a sub-batch of the
+// level-0 decoder chain, see unet_forward).  d_probs / d_logits point at the batch's first tile.
 static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_logits, uint8_t* d_labels,
-                        const TileGrid* grid, cudaStream_t st) {
+                        const TileGrid* grid, cudaStream_t st, int tile0 = 0) {
   UNet* net = ctx->net;
   const LayerDef& l = kLayers[li];
   const Wire& wr = kWires[li];
   const bool bf16 = net->precision == ECSEG_PREC_BF16;
-  const int NT = ctx->max_tiles;
+  const int NT = ctx->max_tiles - tile0;      // tiles addressable behind the offset base pointers
+  auto tile_base = [&](int buf, int hw) -> char* {    // first byte of tile `tile0` in activation buffer `buf`
+    return (char*)net->buf[buf] + (size_t)tile0 * hw * hw * kBufs[buf].ch * 2;
+  };
   if (li == 22) {
     HeadTcParams h;
     memset(&h, 0, sizeof(h));
     const size_t pc = kBufs[wr.in].ch;
-    ECSEG_TRY(make_tm_nhwc(ctx, &h.tm_a, net->buf[wr.in], l.cin, kTile, kTile, NT, pc, pc * kTile, pc * kTile * kTile, 18, 18, bf16));
+    ECSEG_TRY(make_tm_nhwc(ctx, &h.tm_a, tile_base(wr.in, kTile), l.cin, kTile, kTile, NT, pc, pc * kTile, pc * kTile * kTile, 18, 18, bf16));
     ECSEG_TRY(make_tm_wgt(ctx, &h.tm_b, net->w[li], l.cin, 48, 48, bf16));
-    h.n_img = n; h.is_bf16 = bf16;
-    h.probs = d_probs; h.logits = d_logits; h.labels = d_labels;
+    h.n_img = n; h.tile0 = tile0; h.is_bf16 = bf16;
+    const size_t poff = (size_t)tile0 * kTile * kTile * 4;
+    h.probs = d_probs ? d_probs + poff : nullptr; h.logits = d_logits ? d_logits + poff : nullptr; h.labels = d_labels;
     if (grid) h.grid = *grid;
     h.device_error = &ctx->counters->device_error;
     h.range_error = &ctx->counters->range_error;
@@ -602,7 +610,7 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   if (fuse1) cs = getenv("ECSEG_FUSE1_SINGLE") ? 1 : 3;
   const size_t pin = kBufs[wr.in].ch, pout = kBufs[wr.out].ch;
   // halo box: 18 rows x (block width + 2) pixels; transposed convolutions work on 16x8 blocks (conv_tc.cu: blk_w)
-  ECSEG_TRY(make_tm_nhwc(ctx, &p.tm_a, net->buf[wr.in], l.cin, in_hw, in_hw, NT, pin, pin * in_hw, pin * in_hw * in_hw,
+  ECSEG_TRY(make_tm_nhwc(ctx, &p.tm_a, tile_base(wr.in, in_hw), l.cin, in_hw, in_hw, NT, pin, pin * in_hw, pin * in_hw * in_hw,
                          l.convT ? 10 : 18, 18, bf16));
   // weight boxes: a whole tap tile, or the half a CTA of a cluster / pair fetches (32-row boxes for the pair's transposed conv)
   const int box_rows = cs == 1 ? n_tile : (cs == 3 && l.convT ? 32 : n_tile / 2);
@@ -611,12 +619,12 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   if (!l.convT) {
     p.n_acc = 1;
     for (int t = 0; t < 9; ++t) { p.tap_dy[t] = (signed char)(t / 3); p.tap_dx[t] = (signed char)(t % 3); p.tap_acc[t] = 0; }
-    ECSEG_TRY(make_tm_nhwc(ctx, &p.tm_out[0], net->buf[wr.out], (int)pout, out_hw, out_hw, NT, pout, pout * out_hw,
+    ECSEG_TRY(make_tm_nhwc(ctx, &p.tm_out[0], tile_base(wr.out, out_hw), (int)pout, out_hw, out_hw, NT, pout, pout * out_hw,
                            pout * out_hw * out_hw, 8, 16, bf16));
     if (wr.pool_to >= 0) {   // fused 2x2 max pool
       const size_t pp = kBufs[wr.pool_to].ch;
       const int ph = out_hw / 2;
-      ECSEG_TRY(make_tm_nhwc(ctx, &p.tm_pool, net->buf[wr.pool_to], (int)pp, ph, ph, NT, pp, pp * ph, pp * ph * ph, 4, 8, bf16));
+      ECSEG_TRY(make_tm_nhwc(ctx, &p.tm_pool, tile_base(wr.pool_to, ph), (int)pp, ph, ph, NT, pp, pp * ph, pp * ph * ph, 4, 8, bf16));
       p.has_pool = 1;
     }
   } else {
@@ -632,7 +640,7 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
       }
     for (int par = 0; par < 4; ++par) {   // one strided view of the 2x grid per output parity
       const int py = par >> 1, px = par & 1;
-      const char* base = (const char*)net->buf[wr.out] + ((size_t)py * out_hw + px) * pout * esz;
+      const char* base = tile_base(wr.out, out_hw) + ((size_t)py * out_hw + px) * pout * esz;
       ECSEG_TRY(make_tm_nhwc(ctx, &p.tm_out[par], base, (int)pout, in_hw, in_hw, NT, 2 * pout, 2 * pout * out_hw,
                              pout * out_hw * out_hw, 8, 16, bf16));
     }
@@ -677,7 +685,26 @@ int unet_forward(ecseg_ctx* ctx, const uint8_t* d_tiles, const uint8_t* d_pre, c
   net->in_tiles = d_tiles; net->in_pre = d_pre;
   const bool fused_first = prec != ECSEG_PREC_FP32 && net->fuse_first && net->stop_after != 0 && net->tc_cluster == 0 &&
                            net->tc_ntile_max == 0;
+  // Level-0 decoder chain in L2-sized sub-batches (tensor-core modes, OPT-IN: ECSEG_L0_SUBBATCH=<tiles>).  up1 ->
+  // conv1-3 -> conv1-4 -> head move 8.4 MB per tile between each other; over a whole image (100 tiles) every one of
+  // those tensors is 839 MB and makes a round trip through HBM.  Run over `sub` tiles at a time, the consumer finds
+  // most of its producer's output still in the 126 MB L2.  Measured (profiles/r02_exp_l0_subbatch.txt): in short
+  // bursts at ~1.9 GHz, where those kernels are DRAM-bound, the chain drops from 20.9 to 13.7 us per tile, launches
+  // included; in the sustained, power-capped regime the bench measures (~1.47 GHz) the same kernels are no longer
+  // DRAM-bound, the saved DRAM energy buys +3 % clock and the 6x more launches take it back: 116.6 images/s without,
+  // 115.0 with.  Off by default.
+  const int kChainFirst = 19;     // up1
+  const int sub = (prec != ECSEG_PREC_FP32 && net->l0_subbatch > 0 && net->stop_after < 0) ? net->l0_subbatch : 0;
   for (int li = 0; li < 23; ++li) {
+    if (sub > 0 && li == kChainFirst) {
+      const int n_sub = (n + sub - 1) / sub;
+      for (int sb = 0; sb < n_sub; ++sb) {      // equal-sized sub-batches: no short tail launch
+        const int t0 = (int)((long long)n * sb / n_sub), t1 = (int)((long long)n * (sb + 1) / n_sub);
+        for (int lj = kChainFirst; lj < 23; ++lj)
+          ECSEG_TRY(run_layer_tc(ctx, lj, t1 - t0, d_probs, d_logits, d_labels, grid, st, t0));
+      }
+      break;
+    }
     if (li == 0 && fused_first) {
       continue;     // conv1-1 is computed inside conv1-2's halo producer (conv_tc.cu, FUSE1)
     } else if (li == 0) {
