@@ -39,6 +39,7 @@ struct Counters {
   int device_error;                // tcgen05 pipeline watchdog
   int act_overflow;                // 1 + index of the first U-Net layer whose 16-bit output held an inf / NaN (0 = none)
   int pre_ticket;                  // blocks of k_pre_convert_hist that have added their histogram (the last one runs Otsu)
+  int roots_ticket;                // blocks of k_ccl_roots that have finished (the last one writes the count_cc tuple)
   int ov_hits[4];                  // meta_overlay: components flagged per colocalisation test
   int progress[8];                 // tcgen05 pipeline progress markers (ecseg_debug_progress; written by one thread per role)
   // per labelling run, double buffered by run parity (a run clears the other parity's slots for the next run)

@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) k_ccl_tile(const uint8_t* __restrict__ cl
   const int x0 = blockIdx.x * kCclTile, y0 = blockIdx.y * kCclTile;
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4) {     // per-run counters (k_ccl_roots runs later)
     cnt->ncomp[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { cnt->n_chrom = 0; cnt->n_nuc = 0; cnt->last_root = -1; cnt->npix_run[par ^ 1] = 0; }
+    if (threadIdx.x == 0) { cnt->n_chrom = 0; cnt->n_nuc = 0; cnt->last_root = -1; cnt->npix_run[par ^ 1] = 0; cnt->roots_ticket = 0; }
     cnt->ov_hits[threadIdx.x] = 0;
     cnt->npix_cls[par ^ 1][threadIdx.x] = 0;
   }
@@ -381,7 +381,8 @@ __global__ void __launch_bounds__(256) k_ccl_roots(const uint8_t* __restrict__ c
                                                    const int32_t* __restrict__ roots, const int32_t* __restrict__ tile_nroots,
                                                    int32_t* __restrict__ L, int32_t* __restrict__ area,
                                                    unsigned long long* __restrict__ sy, unsigned long long* __restrict__ sx,
-                                                   int32_t* __restrict__ flag, Counters* __restrict__ cnt) {
+                                                   int32_t* __restrict__ flag, Counters* __restrict__ cnt, long long n_px,
+                                                   int32_t* __restrict__ d_n, int64_t* __restrict__ d_px) {
   __shared__ unsigned s_roots[4];
   __shared__ int s_last;
   if (threadIdx.x < 4) s_roots[threadIdx.x] = 0;
@@ -424,9 +425,26 @@ __global__ void __launch_bounds__(256) k_ccl_roots(const uint8_t* __restrict__ c
   // hand the per-run pixel counters over in the layout the rule kernels read
   if (blockIdx.x == 0 && threadIdx.x < 4)
     cnt->npix[threadIdx.x] = threadIdx.x == 0 ? cnt->npix_run[par] : cnt->npix_cls[par][threadIdx.x];
+  // count_cc tuple (image_tools.py:114-119) of this labelling, written by whichever block finishes last -- no
+  // one-thread launch behind the labelling.  np.unique(labels)[1:] drops the smallest label on the assumption that it
+  // is background; with no background pixel at all the single component itself is dropped.
+  if (!(d_n || d_px)) return;       // (uniform)
+  __syncthreads();                  // this block's component counts (threads 0..3 above) precede its ticket
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&cnt->roots_ticket, 1) == (int)gridDim.x - 1) {
+      __threadfence();
+      const int n = *reinterpret_cast<volatile int*>(&cnt->ncomp[1]);
+      long long px = (long long)*reinterpret_cast<volatile unsigned long long*>(&cnt->npix_run[par]);
+      if (n > 0 && px == n_px) px = 0;
+      if (d_n) *d_n = n;
+      if (d_px) *d_px = px;
+    }
+  }
 }
 
-static int ccl_run(ecseg_ctx* ctx, const uint8_t* cls, int h, int w, int mode, int c, int conn8, int what, cudaStream_t st) {
+static int ccl_run(ecseg_ctx* ctx, const uint8_t* cls, int h, int w, int mode, int c, int conn8, int what, cudaStream_t st,
+                   int32_t* d_n = nullptr, int64_t* d_px = nullptr) {
   if ((size_t)cdiv(w, kCclTile) * cdiv(h, kCclTile) > ctx->max_ccl_tiles) {
     ctx->err = "labelling: image aspect ratio needs more 32x32 tiles than the context was sized for";
     return ECSEG_E_INVALID;
@@ -452,7 +470,7 @@ static int ccl_run(ecseg_ctx* ctx, const uint8_t* cls, int h, int w, int mode, i
   }
   const int n_tiles = cdiv(w, kCclTile) * cdiv(h, kCclTile);
   k_ccl_roots<<<cdiv(n_tiles, 8), 256, 0, st>>>(cls, n_tiles, mode, c, what, par, ctx->root_list, ctx->tile_nroots, ctx->L, ctx->area,
-                                                ctx->sum_y, ctx->sum_x, ctx->flag, ctx->counters);
+                                                ctx->sum_y, ctx->sum_x, ctx->flag, ctx->counters, (long long)h * w, d_n, d_px);
   ECSEG_CHECK_LAUNCH();
   return ECSEG_OK;
 }
@@ -562,6 +580,66 @@ __global__ void __launch_bounds__(128) k_ec_dilate(const uint8_t* __restrict__ s
   }
 }
 
+// size_thresh's three rules (image_tools.py:41-59) for one pixel from the labelling snapshot: the value the pixel has
+// after `size_thresh(img)`.  Same integer tests as k_size_apply.
+struct SizeRule {
+  long long n2, n3, s2, s3;
+  __device__ __forceinline__ int operator()(int v, int i, const int32_t* __restrict__ L, const int32_t* __restrict__ area) const {
+    if (v == 0) return 0;
+    const long long a = area[root_of(L, i)];
+    if (v == 1) return (n2 > 0 && a * n2 < s2) ? 0 : 1;
+    if (v == 2) return (n3 > 0 && a * n3 < s3) ? 3 : 2;
+    return a < kEcSizeThreshold ? 0 : 3;
+  }
+};
+
+// size_thresh's apply pass and the ecDNA boundary erase (image_tools.py:62,64) in one kernel: the erase is a 3x3-cross
+// stencil on the image AFTER size_thresh, so every pixel of the stencil is put through the size rule on the fly (label
+// and area look-ups only where the pixel is not background) instead of in a pass of its own.  src is the map the
+// labelling was made from (untouched), dst receives size_thresh + erase.
+__global__ void __launch_bounds__(128) k_size_erase(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int h, int w,
+                                                    const int32_t* __restrict__ L, const int32_t* __restrict__ area,
+                                                    const Counters* __restrict__ cnt) {
+  ROW4_XY();
+  SizeRule rule = {cnt->ncomp[2], cnt->ncomp[3], (long long)cnt->npix[2], (long long)cnt->npix[3]};
+  const int base = y * w;
+  const uint8_t* row = src + (size_t)base;
+  int vc[6];   // values after size_thresh of x4-1 .. x4+4 in this row (-1: outside the image)
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { const int x = x4 - 1 + k; vc[k] = (x >= 0 && x < w) ? rule(row[x], base + x, L, area) : -1; }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = x4 + k;
+    if (x >= w) break;
+    const bool c = vc[k + 1] == 3, lf = vc[k] == 3, rt = vc[k + 2] == 3;
+    const bool up = y > 0 ? rule(row[x - w], base - w + x, L, area) == 3 : false;
+    const bool dn = y < h - 1 ? rule(row[x + w], base + w + x, L, area) == 3 : false;
+    const bool dil = c || up || dn || lf || rt;
+    const bool ero = c && (y > 0 ? up : true) && (y < h - 1 ? dn : true) && (x > 0 ? lf : true) && (x < w - 1 ? rt : true);
+    dst[(size_t)base + x] = (dil != ero) ? 0 : (uint8_t)vc[k + 1];
+  }
+}
+
+// nucleus-in-metaphase apply pass and the final ecDNA dilation (image_tools.py:81,83) in one kernel: the dilation only
+// looks at ecDNA pixels, which the nucleus rule never touches, so the two compose pixel by pixel.
+__global__ void __launch_bounds__(128) k_nucleus_dilate(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int h, int w,
+                                                        const int32_t* __restrict__ L, const int32_t* __restrict__ flag) {
+  ROW4_XY();
+  const uint8_t* row = src + (size_t)y * w;
+  bool e[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { const int x = x4 - 1 + k; e[k] = (x >= 0 && x < w) ? row[x] == 3 : false; }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = x4 + k;
+    if (x >= w) break;
+    const bool d = e[k + 1] || e[k] || e[k + 2] || (y > 0 && row[x - w] == 3) || (y < h - 1 && row[x + w] == 3);
+    uint8_t v = row[x];
+    if (!d && v == 1 && flag[root_of(L, y * w + x)]) v = 0;      // nucleus component inside a metaphase spread
+    dst[(size_t)y * w + x] = d ? 3 : v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // nucleus-in-metaphase removal  (image_tools.py:66-81)
 // ------------------------------------------------------------------------------------------------
@@ -644,7 +722,7 @@ __global__ void __launch_bounds__(256) k_nucleus_apply(uint8_t* __restrict__ cls
     if (k < n && v[k] == 1 && flag[root_of(L, (int)(i0 + k))]) cls[i0 + k] = 0;     // nuclei are few: scattered byte stores
 }
 
-static int pp_nucleus_in_metaphase(ecseg_ctx* ctx, uint8_t* cls, int h, int w, cudaStream_t st) {
+static int pp_nucleus_in_metaphase(ecseg_ctx* ctx, uint8_t* cls, int h, int w, cudaStream_t st, bool apply = true) {
   ECSEG_TRY(ccl_run(ctx, cls, h, w, KEY_CLASS, 0, /*conn8=*/1, FIN_AREA | FIN_CENTROID, st));
   const int n_tiles = cdiv(w, kCclTile) * cdiv(h, kCclTile);
   k_compact_centroids<<<cdiv(n_tiles, 8), 256, 0, st>>>(cls, n_tiles, ctx->root_list, ctx->tile_nroots, ctx->L, ctx->area, ctx->sum_y,
@@ -653,6 +731,7 @@ static int pp_nucleus_in_metaphase(ecseg_ctx* ctx, uint8_t* cls, int h, int w, c
   k_nucleus_decide<<<296, 256, 0, st>>>(ctx->nuc_roots, ctx->chrom_cy, ctx->chrom_cx, ctx->area, ctx->sum_y,
                                         ctx->sum_x, ctx->flag, ctx->counters);
   ECSEG_CHECK_LAUNCH();
+  if (!apply) return ECSEG_OK;       // the caller applies flag[] itself (fused with the final dilation)
   k_nucleus_apply<<<flat_blocks((long long)h * w), 256, 0, st>>>(cls, (long long)h * w, ctx->L, ctx->flag);
   ECSEG_CHECK_LAUNCH();
   return ECSEG_OK;
@@ -727,23 +806,9 @@ int pp_merge_comp(ecseg_ctx* ctx, uint8_t* cls, int h, int w, int c, cudaStream_
 // ------------------------------------------------------------------------------------------------
 // count_cc  (image_tools.py:114-119)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_count_finish(const Counters* __restrict__ cnt, long long n_px, int32_t* d_n, int64_t* d_px) {
-  if (threadIdx.x || blockIdx.x) return;
-  const int n = cnt->ncomp[1];
-  long long px = (long long)cnt->npix[0];
-  // np.unique(labels)[1:] drops the smallest label on the assumption that it is background; with no
-  // background pixel at all the single component itself is dropped.
-  if (n > 0 && px == n_px) px = 0;
-  if (d_n) *d_n = n;
-  if (d_px) *d_px = px;
-}
-
 static int count_mode(ecseg_ctx* ctx, const uint8_t* cls, int h, int w, int mode, int c, int32_t* d_n, int64_t* d_px,
                       cudaStream_t st) {
-  ECSEG_TRY(ccl_run(ctx, cls, h, w, mode, c, /*conn8=*/1, 0, st));
-  k_count_finish<<<1, 32, 0, st>>>(ctx->counters, (long long)h * w, d_n, d_px);
-  ECSEG_CHECK_LAUNCH();
-  return ECSEG_OK;
+  return ccl_run(ctx, cls, h, w, mode, c, /*conn8=*/1, 0, st, d_n, d_px);     // the tuple comes out of k_ccl_roots
 }
 
 int pp_count_cc(ecseg_ctx* ctx, const uint8_t* d_mask, int h, int w, int32_t* d_n, int64_t* d_px, cudaStream_t st) {
@@ -931,15 +996,25 @@ static int pp_postprocess_launches(ecseg_ctx* ctx, uint8_t* cls, int h, int w, i
   uint8_t* t = ctx->tmp_a;
   ECSEG_TRY(pp_fill_holes(ctx, cls, h, w, 1, st));                       // :61
   ECSEG_TRY(pp_fill_holes(ctx, cls, h, w, 2, st));                       // :61
-  ECSEG_TRY(pp_size_thresh(ctx, cls, h, w, st));                         // :62
-  k_ec_boundary_erase<<<row4_grid(h, w), 128, 0, st>>>(cls, t, h, w);  // :64   cls -> t
-  ECSEG_CHECK_LAUNCH();
-  ECSEG_TRY(pp_nucleus_in_metaphase(ctx, t, h, w, st));                  // :66-81
-  if (flags & ECSEG_PP_FAITHFUL_MERGE) {                                 // :82 (no-op here)
+  static const bool unfused = getenv("ECSEG_PP_UNFUSED") != nullptr;     // A/B: every rule as a pass of its own
+  if (unfused) {
+    ECSEG_TRY(pp_size_thresh(ctx, cls, h, w, st));                         // :62
+    k_ec_boundary_erase<<<row4_grid(h, w), 128, 0, st>>>(cls, t, h, w);  // :64   cls -> t
+    ECSEG_CHECK_LAUNCH();
+  } else {
+    // :62 + :64   labelling snapshot of cls, then size rules and boundary erase in one pass, cls -> t
+    ECSEG_TRY(ccl_run(ctx, cls, h, w, KEY_CLASS, 0, /*conn8=*/1, FIN_AREA | FIN_CLASS_PIX, st));
+    k_size_erase<<<row4_grid(h, w), 128, 0, st>>>(cls, t, h, w, ctx->L, ctx->area, ctx->counters);
+    ECSEG_CHECK_LAUNCH();
+  }
+  const bool merge = (flags & ECSEG_PP_FAITHFUL_MERGE) != 0;
+  ECSEG_TRY(pp_nucleus_in_metaphase(ctx, t, h, w, st, /*apply=*/merge || unfused));   // :66-81
+  if (merge) {                                                           // :82 (no-op here)
     ECSEG_TRY(pp_merge_comp(ctx, t, h, w, 1, st));
     ECSEG_TRY(pp_merge_comp(ctx, t, h, w, 2, st));
   }
-  k_ec_dilate<<<row4_grid(h, w), 128, 0, st>>>(t, cls, h, w);       // :83   t -> cls
+  if (merge || unfused) k_ec_dilate<<<row4_grid(h, w), 128, 0, st>>>(t, cls, h, w);       // :83   t -> cls
+  else k_nucleus_dilate<<<row4_grid(h, w), 128, 0, st>>>(t, cls, h, w, ctx->L, ctx->flag);  // :81 + :83
   ECSEG_CHECK_LAUNCH();
   if (d_n_ec || d_ec_px) ECSEG_TRY(count_mode(ctx, cls, h, w, KEY_EQ, 3, d_n_ec, d_ec_px, st));  // metaseg.py:46
   return ECSEG_OK;

@@ -130,7 +130,7 @@ def test_graph_replay_same_buffers_different_maps(eng, golden):
         per_call.append(eng.launch_count() - l0)
         assert np.array_equal(buf.cpu().numpy(), want), seed
         assert (int(n.item()), int(px.item())) == mo.count_cc(want == 3), seed
-    assert len(set(per_call)) == 1 and per_call[0] >= 20, per_call       # replays account for the same launches
+    assert len(set(per_call)) == 1 and per_call[0] >= 15, per_call       # replays account for the same launches
     # golden cases through the graph path too (fresh buffers: captured, launched once, evicted from the bounded cache)
     g = golden("postproc")
     with torch.cuda.stream(s):
