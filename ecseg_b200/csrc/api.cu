@@ -481,6 +481,11 @@ int ecseg_activation_overflow(ecseg_ctx* ctx, int* layer) {
   return v ? overflow_error(ctx, v) : ECSEG_OK;
 }
 
+int ecseg_unet_work(int h, int w, int labels_only, double* flops_reference, double* flops_executed) {
+  static const bool no_skip = getenv("ECSEG_NO_OWNER_SKIP") != nullptr && atoi(getenv("ECSEG_NO_OWNER_SKIP")) != 0;
+  return unet_work(h, w, labels_only && !no_skip, flops_reference, flops_executed);
+}
+
 int ecseg_last_stage_ms(ecseg_ctx* ctx, float ms[4]) {
   API_GUARD(ctx);
   if (!ctx->ev_valid || !ms) { if (ctx) ctx->err = "last_stage_ms: no segment_image call yet"; return ECSEG_E_STATE; }

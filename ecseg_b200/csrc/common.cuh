@@ -207,5 +207,6 @@ int unet_load_weights(ecseg_ctx* ctx, const float* blob, size_t n, int precision
 int unet_forward(ecseg_ctx* ctx, const uint8_t* d_tiles, const uint8_t* d_pre, const TileGrid* grid, int n,
                  float* d_probs, float* d_logits, uint8_t* d_labels, cudaStream_t st);
 int unet_debug_layer(ecseg_ctx* ctx, int layer, int n, float* d_out, cudaStream_t st);
+int unet_work(int h, int w, int skip_unowned, double* ref, double* exec);
 
 }  // namespace ecseg

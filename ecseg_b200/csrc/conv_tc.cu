@@ -196,6 +196,22 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
   const int n_mblocks = p.n_img * bh * bw;
   const int n_mgroups = (n_mblocks + CS - 1) / CS;
   const int n_items = n_mgroups * p.n_chunks;
+  // M block index -> tile, block row / column.  A work-listed launch (p.work) visits the block columns of a row in
+  // owned_col order, so that the two margin columns form one CTA pair.
+  auto block_of = [&](int mb, int& img, int& by, int& bx) {
+    img = mb / (bh * bw);
+    const int rem = mb - img * (bh * bw);
+    by = rem / bw;
+    const int bxp = rem - by * bw;
+    bx = p.work ? owned_col(bxp, bw) : bxp;
+  };
+  // The CTA's (cluster's) k-th unit of work: every item in turn, or the k-th entry of the work list.  `keep` has bit r set
+  // when CTA r of the cluster stores its block.
+  const int n_units = p.work ? p.n_work : n_items;
+  auto unit = [&](int k, int& it, int& keep) {
+    if (p.work) { const int e = p.work[k]; it = (e & kWorkItemMask) - p.work_base; keep = (e >> 28) & ((1 << CS) - 1); }
+    else { it = k; keep = (1 << CS) - 1; }
+  };
 
   // Producer and MMA roles run as WHOLE warps with warp-uniform control flow: every lane waits on the
   // mbarriers, one elected lane issues.  That keeps descriptors / coordinates in uniform registers
@@ -208,13 +224,17 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
     bool ok = true;
     int kit = 0;
     if (!FUSE1) grid_dep_wait();          // the halos are the previous layer's output (FUSE1: this warp loads weights only)
-    for (int it = cluster_id; it < n_items && ok; it += n_clusters, ++kit) {
+    bool first = true;                      // first item this CTA processes (resident weights are loaded with it)
+    for (int k = cluster_id; k < n_units && ok; k += n_clusters, ++kit) {
+      int it, keep;
+      unit(k, it, keep);
       if (leader) stamp(0, kit, 0);
       const int mg = it % n_mgroups, nch = it / n_mgroups;
       int mb = mg * CS + (int)rank;
       if (mb >= n_mblocks) mb = n_mblocks - 1;    // ghost CTA of an odd tail: same loads, no stores
-      const int img = mb / (bh * bw), rem = mb % (bh * bw);
-      const int y0 = (rem / bw) << 4, x0 = (rem % bw) * kBlkW;
+      int img, by, bx;
+      block_of(mb, img, by, bx);
+      const int y0 = by << 4, x0 = bx * kBlkW;
       for (int ch = 0; ch < p.cin_chunks && ok; ++ch) {
         if (!FUSE1) ok = __all_sync(0xffffffffu, mbar_wait(empty_a(sa), pa ^ 1, p.device_error, 1));
         if (!ok) break;
@@ -234,7 +254,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
         if (NACC == 1) {
           // resident weights (b_resident: the layer's 9 tap tiles fit the 9 weight stages): loaded once, for the CTA's
           // first item, and reused by every later item -- the L2 -> SM stream is then the halo alone
-          for (int t = 0; t < 9 && !(p.b_resident && it != cluster_id); ++t) {
+          for (int t = 0; t < 9 && !(p.b_resident && !first); ++t) {
             ok = __all_sync(0xffffffffu, mbar_wait(empty_b(sb), pb ^ 1, p.device_error, 2));
             if (!ok) break;
             if (leader) {
@@ -259,7 +279,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
           //  first item only, the stage index still walks them so every later item finds its views in place)
 #pragma unroll
           for (int v = 0; v < kNumViews; ++v) {
-            if (p.b_resident && it != cluster_id) { if (++sb == BS) { sb = 0; pb ^= 1; } continue; }
+            if (p.b_resident && !first) { if (++sb == BS) { sb = 0; pb ^= 1; } continue; }
             ok = __all_sync(0xffffffffu, mbar_wait(empty_b(sb), pb ^ 1, p.device_error, 2));
             if (!ok) break;
             if (leader && PAIR) {
@@ -302,6 +322,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
         }
       }
       if (leader) stamp(0, kit, 2);                      // all loads of the item issued
+      first = false;
     }
   } else if (warp == 1 && (!PAIR || rank == 0)) {
     // ===================== MMA issuer (the leader CTA's for a pair) =====================
@@ -323,7 +344,8 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
     int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
     bool ok = true;
     int kit = 0;
-    for (int it = cluster_id; it < n_items && ok; it += n_clusters, ++kit) {
+    bool first = true;
+    for (int k = cluster_id; k < n_units && ok; k += n_clusters, ++kit) {
       if (leader) stamp(1, kit, 0);
       ok = __all_sync(0xffffffffu, mbar_wait(tmem_empty(as), pacc ^ 1, p.device_error, 3));
       if (!ok) break;
@@ -338,7 +360,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
         if (NACC == 1) {
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
-            if (!p.b_resident || it == cluster_id) ok = __all_sync(0xffffffffu, mbar_wait(full_b(sb), pb, p.device_error, 5));
+            if (!p.b_resident || first) ok = __all_sync(0xffffffffu, mbar_wait(full_b(sb), pb, p.device_error, 5));
             if (!ok) break;
             tc_fence_after();
             const uint32_t b_lo = sdesc_lo(b_base + sb * kBStage);
@@ -363,7 +385,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
           const uint32_t idesc4 = make_idesc(kM, 4 * N_TILE, BF16), idesc2 = make_idesc(kM, 2 * N_TILE, BF16);
 #pragma unroll
           for (int v = 0; v < kNumViews; ++v) {
-            if (!p.b_resident || it == cluster_id) ok = __all_sync(0xffffffffu, mbar_wait(full_b(sb), pb, p.device_error, 5));
+            if (!p.b_resident || first) ok = __all_sync(0xffffffffu, mbar_wait(full_b(sb), pb, p.device_error, 5));
             if (!ok) break;
             tc_fence_after();
             const uint32_t b_lo = sdesc_lo(b_base + sb * kBStage);
@@ -398,9 +420,10 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
         if (++sa == AS) { sa = 0; pa ^= 1; }
       }
       if (leader) commit_all(tmem_full(as), /*local_only=*/true);     // accumulators complete -> epilogue
-      if (leader) mark(1, it + 1);
+      if (leader) mark(1, k + 1);
       if (leader) stamp(1, kit, 3);                      // every MMA of the item issued
       __syncwarp();
+      first = false;
       if (++as == kAccStages) { as = 0; pacc ^= 1; }
     }
   } else if (FUSE1 && warp >= kGenWarp0) {
@@ -601,20 +624,25 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
     // non-negative halves the fp16 / bf16 order is the integer order).  An exponent of all ones -- inf from the
     // conversion's overflow, or a NaN -- shows as a pattern >= 0x7C00 (fp16) / 0x7F80 (bf16); checked once, below.
     uint32_t mx = 0;
-    for (int it = cluster_id; it < n_items && ok; it += n_clusters, ++kit) {
+    for (int k = cluster_id; k < n_units && ok; k += n_clusters, ++kit) {
+      int it, keep;
+      unit(k, it, keep);
       if (e0) stamp(2 + eg, kit, 0);
       const int mg = it % n_mgroups, nch = it / n_mgroups;
       const int mb_raw = mg * CS + (int)rank;
-      const bool ghost = mb_raw >= n_mblocks;
-      const int mb = ghost ? n_mblocks - 1 : mb_raw;
-      const int img = mb / (bh * bw), rem = mb % (bh * bw);
-      const int y0 = (rem / bw) << 4, x0 = (rem % bw) * kBlkW;
+      // no stores for the ghost CTA of an odd tail, nor for a block in the unowned margin whose pair partner is needed
+      const bool ghost = mb_raw >= n_mblocks || !((keep >> rank) & 1);
+      const int mb = mb_raw >= n_mblocks ? n_mblocks - 1 : mb_raw;
+      int img, by, bx;
+      block_of(mb, img, by, bx);
+      const int y0 = by << 4, x0 = bx * kBlkW;
       ok = mbar_wait<64>(tmem_full(as), pacc, p.device_error, 6);
       if (!ok) break;
       if (e0) stamp(2 + eg, kit, 1);                     // accumulators complete
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccCols);
       int unit = 0;
+      uint32_t mxi = 0;                      // this item's part of the range guard (blocks that are not stored do not count)
 #pragma unroll 1
       for (int acc = 0; acc < NACC; ++acc) {
 #pragma unroll 1
@@ -641,10 +669,10 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
               uint32_t o[16];     // ReLU (models.py:20) rides on the 16-bit conversion
               if (p.relu) {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) { o[k] = pack2_relu(f[2 * k], f[2 * k + 1], BF16); mx = __vmaxu2(mx, o[k]); }
+                for (int k = 0; k < 16; ++k) { o[k] = pack2_relu(f[2 * k], f[2 * k + 1], BF16); mxi = __vmaxu2(mxi, o[k]); }
               } else {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) { o[k] = pack2(f[2 * k], f[2 * k + 1], BF16); mx = __vmaxu2(mx, o[k] & 0x7fff7fffu); }
+                for (int k = 0; k < 16; ++k) { o[k] = pack2(f[2 * k], f[2 * k + 1], BF16); mxi = __vmaxu2(mxi, o[k] & 0x7fff7fffu); }
               }
 #pragma unroll
               for (int k = 0; k < 4; ++k)
@@ -681,6 +709,7 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
           }
         }
       }
+      if (!ghost) mx = __vmaxu2(mx, mxi);
       tc_fence_before();
       if (e0) stamp(2 + eg, kit, 2);                     // this group's units stored
       if (e0 && eg == 0) mark(2, it + 1);
@@ -734,7 +763,8 @@ int launch_impl(ecseg_ctx* ctx, ConvTcParams& p, cudaStream_t st) {
     attr_done = true;
   }
   const int n_mblocks = p.n_img * (p.H >> 4) * (p.W / blk_w(NACC));
-  const int n_items = ((n_mblocks + CS - 1) / CS) * p.n_chunks;
+  const int n_items = p.work ? p.n_work : ((n_mblocks + CS - 1) / CS) * p.n_chunks;
+  if (p.work && (FUSE1 || p.n_chunks != 1 || p.n_work < 1)) { ctx->err = "conv_tc: a work list needs a plain single-chunk layer"; return ECSEG_E_INVALID; }
   int clusters = ctx->n_sms / CS;
   if (n_items < clusters) clusters = n_items;
   cudaLaunchConfig_t cfg = {};

@@ -8,6 +8,32 @@ namespace ecseg {
 
 constexpr int kMaxPar = 4;   // output-parity classes of a stride-2 transposed conv
 constexpr int kMaxTaps = 9;
+constexpr int kMaxGridAxis = 40;   // tile rows / columns an OwnedBlocks table covers (images up to ~8000 px per axis)
+
+// Which M blocks of a tile a layer has to compute when only the pixels the stitcher will actually take from that tile
+// (its "owned" region, image_tools.py:188-252 / stitch.cuh axis_owner) matter downstream.  The 256x256 tiles overlap by
+// 25 px and a tile owns only ~206x206 of its own prediction; the last layers of the network have a receptive field of a
+// few pixels, so their blocks that lie entirely in the unowned margin are dead work: the head needs conv1-4 only on
+// owned +-1 px, conv1-4 needs conv1-3 on owned +-2, conv1-3 needs up1 on owned +-3.  Per tile row index ri (column
+// index ci) of the image's tile grid: the half-open range of needed block rows (columns), in the layer's own block units.
+// (host side: unet.cu builds a compact WORK LIST of the needed items from it, so that the persistent CTAs share the
+//  remaining work evenly and test nothing per item)
+struct OwnedBlocks {
+  int on;
+  int nr;                 // tile rows of the grid: tile index = ci * nr + ri
+  unsigned char r_lo[kMaxGridAxis], r_hi[kMaxGridAxis], c_lo[kMaxGridAxis], c_hi[kMaxGridAxis];
+  bool needed(int tile, int by, int bx) const {
+    const int ci = tile / nr, ri = tile - ci * nr;
+    return by >= r_lo[ri] && by < r_hi[ri] && bx >= c_lo[ci] && bx < c_hi[ci];
+  }
+};
+// Order of the block columns within a block row of a work-listed layer: the two outermost columns -- the ones that fall
+// into the unowned margin -- come first, so that a CTA pair (two consecutive blocks of the order) gets both and the
+// pair's item can be dropped as a whole.
+__host__ __device__ __forceinline__ int owned_col(int bxp, int bw) { return bxp == 0 ? 0 : (bxp == 1 ? bw - 1 : bxp - 1); }
+// Work list entry: item index (M group of the launch) in the low 28 bits, bit 28 + r set when the block of CTA r of the
+// pair is needed (a block that is not needed is computed with its partner but not stored).
+constexpr int kWorkItemMask = 0x0fffffff;
 
 // One convolution layer as the kernel sees it.  The GEMM is
 //   D[pixel, cout] = sum over (tap, cin)  A[pixel shifted by tap, cin] * W[tap, cout, cin]
@@ -40,6 +66,9 @@ struct ConvTcParams {
   int* device_error;      // watchdog flag (Counters::device_error)
   int* act_overflow;      // Counters::act_overflow: set to layer_id by the first layer whose 16-bit output holds an inf / NaN
   int layer_id;           // 1 + layer index (spec.UNET_LAYERS)
+  const int* work;        // nullable: compact list of the items to compute (labels-only path: blocks in the unowned tile
+  int n_work;             //   margin are dropped); block columns are then visited in owned_col order
+  int work_base;          // subtracted from a list entry's item index (the list indexes the whole image, a launch a sub-batch)
   int* progress;          // Counters::progress (nullable): role progress markers of CTA 0 for ecseg_debug_progress
   long long* trace;       // nullable: clock64 stamps of CTA 0, [role kTraceRoles][item kTraceItems][stamp 4] (ecseg_debug_trace)
   // conv1-1 fused in front of this layer (conv1-2 only; first_src == nullptr: off).  The halo stages are then computed
@@ -68,6 +97,9 @@ struct HeadTcParams {
   TileGrid grid;
   int* device_error;
   int* range_error;  // Counters::range_error: a probability outside [-1, 1] or NaN (img_as_ubyte raises, src/utils.py:117)
+  const int* work;   // nullable: compact list of the 16x16 blocks (index within the image) that hold an owned pixel
+  int n_work;
+  int work_base;     // index of the launch's first block within the image
 };
 int head_tc_launch(ecseg_ctx* ctx, const HeadTcParams& p, cudaStream_t st);
 

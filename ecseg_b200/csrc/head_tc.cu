@@ -84,6 +84,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_head_tc(const __grid_constant__
   grid_dep_launch();     // programmatic dependent launch, see conv_tc.cu
   constexpr int kBlocksPerImg = (kTile / 16) * (kTile / 16);
   const int n_work = p.n_img * kBlocksPerImg;
+  // the CTA's units of work: every block of the launch in turn, or the entries of the work list (labels-only path:
+  // the blocks that hold a pixel the stitcher takes from their tile)
+  const int n_units = p.work ? p.n_work : n_work;
+  auto unit = [&](int k) -> int { return p.work ? p.work[k] - p.work_base : k; };
 
   // whole-warp roles with warp-uniform control flow, one elected lane issues (see conv_tc.cu)
   if (warp == 0) {
@@ -95,7 +99,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_head_tc(const __grid_constant__
     }
     int sa = 0, pa = 0;
     grid_dep_wait();     // conv1-4's output (the weights above are constants)
-    for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+    for (int un = blockIdx.x; un < n_units; un += gridDim.x) {
+      const int wk = unit(un);
       const int img = wk / kBlocksPerImg, rem = wk % kBlocksPerImg;
       const int y0 = (rem / (kTile / 16)) << 4, x0 = (rem % (kTile / 16)) << 4;
       if (!__all_sync(0xffffffffu, mbar_wait(empty_a(sa), pa ^ 1, p.device_error, 11))) break;
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_head_tc(const __grid_constant__
     const uint32_t b_lo = sdesc_lo(b_base);
     int sa = 0, pa = 0, as = 0, pacc = 0;
     bool ok = __all_sync(0xffffffffu, mbar_wait(full_b, 0, p.device_error, 12));
-    for (int wk = blockIdx.x; wk < n_work && ok; wk += gridDim.x) {
+    for (int un = blockIdx.x; un < n_units && ok; un += gridDim.x) {
       ok = __all_sync(0xffffffffu, mbar_wait(tmem_empty(as), pacc ^ 1, p.device_error, 13));
       if (!ok) break;
       ok = __all_sync(0xffffffffu, mbar_wait(full_a(sa), pa, p.device_error, 14));
@@ -143,8 +148,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_head_tc(const __grid_constant__
     float* zg = zs + g * (kHalo * kZPitch);
     uint32_t pacc = 0;
     int k = 0;
-    for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x, ++k) {
+    for (int un = blockIdx.x; un < n_units; un += gridDim.x, ++k) {
       if ((k & 1) != g) continue;
+      const int wk = unit(un);
       const int img = wk / kBlocksPerImg, rem = wk % kBlocksPerImg;
       const int y0 = (rem / (kTile / 16)) << 4, x0 = (rem % (kTile / 16)) << 4;
       if (!mbar_wait<32>(tmem_full(g), pacc, p.device_error, 15)) break;
@@ -217,7 +223,8 @@ int head_tc_launch(ecseg_ctx* ctx, const HeadTcParams& p, cudaStream_t st) {
     ECSEG_CUDA(cudaFuncSetAttribute(k_head_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_done = true;
   }
-  const int n_work = p.n_img * (kTile / 16) * (kTile / 16);
+  const int n_work = p.work ? p.n_work : p.n_img * (kTile / 16) * (kTile / 16);
+  if (p.work && p.n_work < 1) { ctx->err = "head_tc: empty work list"; return ECSEG_E_INVALID; }
   const int grid = n_work < ctx->n_sms ? n_work : ctx->n_sms;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);

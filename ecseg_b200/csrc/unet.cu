@@ -9,6 +9,7 @@
 //   * bf16 / fp16 : tcgen05 implicit GEMM (conv_tc.cu) -- throughput mode.
 // Activations are NHWC; skip connections are written straight into the first half of the concat
 // buffer and the transposed convolutions into the second half, so no concat kernel exists.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -52,7 +53,10 @@ const Wire kWires[23] = {
 
 }  // namespace
 
+struct WorkLists;      // work lists of the level-0 decoder chain for the current image shape (below)
+
 struct UNet {
+  WorkLists* work_lists = nullptr;
   int precision = -1;
   int esize = 0;  // bytes per activation element
   void* buf[kNumBufs] = {};
@@ -69,6 +73,7 @@ struct UNet {
   int fuse_first = 1;
   const uint8_t* in_tiles = nullptr;  // inputs of the forward in flight (read by the fused first layer)
   const uint8_t* in_pre = nullptr;
+  int skip_unowned = 1;               // skip blocks in the unowned tile margin in the labels-only path (ECSEG_NO_OWNER_SKIP=1: off)
   int l0_subbatch = 0;                // tiles per sub-batch of the level-0 decoder chain (0 = whole batch; ECSEG_L0_SUBBATCH)
 };
 
@@ -355,11 +360,16 @@ static void fill_taps(P& p, bool convT) {
 // ------------------------------------------------------------------------------------------------
 // lifetime
 // ------------------------------------------------------------------------------------------------
+static WorkLists* new_work_lists();
+static void free_work_lists(WorkLists* wl);
+
 int unet_create(ecseg_ctx* ctx) {
   ctx->net = new UNet();
   if (const char* e = getenv("ECSEG_TC_CLUSTER")) { const int v = atoi(e); if (v >= 1 && v <= 3) ctx->net->tc_cluster = v; }
   if (const char* e = getenv("ECSEG_TC_NTILE_MAX")) ctx->net->tc_ntile_max = atoi(e);
   if (const char* e = getenv("ECSEG_NO_FUSE_FIRST")) ctx->net->fuse_first = atoi(e) ? 0 : 1;
+  if (const char* e = getenv("ECSEG_NO_OWNER_SKIP")) ctx->net->skip_unowned = atoi(e) ? 0 : 1;
+  ctx->net->work_lists = new_work_lists();
   if (const char* e = getenv("ECSEG_L0_SUBBATCH")) { const int v = atoi(e); if (v >= 0 && v <= 4096) ctx->net->l0_subbatch = v; }
   return ECSEG_OK;
 }
@@ -377,6 +387,7 @@ static void free_net_buffers(UNet* n) {
 
 void unet_destroy(ecseg_ctx* ctx) {
   if (!ctx->net) return;
+  free_work_lists(ctx->net->work_lists);
   free_net_buffers(ctx->net);
   delete ctx->net;
   ctx->net = nullptr;
@@ -406,6 +417,9 @@ int unet_load_weights(ecseg_ctx* ctx, const float* blob, size_t n_floats, int pr
   for (int i = 0; i < kNumBufs; ++i) {
     const size_t hw = (size_t)(kTile >> kBufs[i].level) * (kTile >> kBufs[i].level);
     ECSEG_CUDA(cudaMalloc(&net->buf[i], (size_t)ctx->max_tiles * hw * kBufs[i].ch * net->esize));
+    // blocks skipped in the unowned margin are never written; their neighbours' halo loads read them (into outputs nobody
+    // uses), so what they hold must at least be finite numbers
+    ECSEG_CUDA(cudaMemset(net->buf[i], 0, (size_t)ctx->max_tiles * hw * kBufs[i].ch * net->esize));
   }
   ECSEG_CUDA(cudaMalloc(&net->debug_dump, 2 * 128 * 256 * sizeof(float)));
 
@@ -508,6 +522,130 @@ int unet_load_weights(ecseg_ctx* ctx, const float* blob, size_t n_floats, int pr
 }
 
 // ------------------------------------------------------------------------------------------------
+// ownership-aware block skipping (conv_tc.cuh OwnedBlocks)
+// ------------------------------------------------------------------------------------------------
+// Pixel range [lo, hi) of tile i, in TILE coordinates, that the stitcher takes from it along one axis: the closed form
+// of image_tools.py:188-252 (stitch.cuh axis_owner) evaluated over the tile's extent.
+static void owned_range(int len, int n, int rem, int i, int& lo, int& hi) {
+  const int start = (i == n - 1 && rem) ? len - kTile : kCore * i;
+  lo = kTile; hi = 0;
+  for (int t = start; t < start + kTile && t < len; ++t)
+    if (axis_owner(t, len, n, rem) == i) { lo = std::min(lo, t - start); hi = std::max(hi, t - start + 1); }
+  if (hi <= lo) { lo = 0; hi = 0; }
+}
+
+// Blocks of `bs_r` x `bs_c` OUTPUT pixels a layer must compute so that its output is valid on owned +- margin.
+static OwnedBlocks owned_blocks(const TileGrid& g, int margin, int bs_r, int bs_c) {
+  OwnedBlocks ob;
+  memset(&ob, 0, sizeof(ob));
+  if (g.nr > kMaxGridAxis || g.nc > kMaxGridAxis) return ob;      // (on == 0: compute everything)
+  ob.on = 1; ob.nr = g.nr;
+  auto fill = [&](int len, int n, int rem, int bs, unsigned char* blo, unsigned char* bhi) {
+    for (int i = 0; i < n; ++i) {
+      int lo, hi;
+      owned_range(len, n, rem, i, lo, hi);
+      if (hi <= lo) { blo[i] = 0; bhi[i] = 0; continue; }
+      blo[i] = (unsigned char)(std::max(0, lo - margin) / bs);
+      bhi[i] = (unsigned char)((std::min(kTile, hi + margin) - 1) / bs + 1);
+    }
+  };
+  fill(g.h, g.nr, g.rem_r, bs_r, ob.r_lo, ob.r_hi);
+  fill(g.w, g.nc, g.rem_c, bs_c, ob.c_lo, ob.c_hi);
+  return ob;
+}
+
+// margins of the level-0 decoder chain: the head computes owned pixels, conv1-4 owned +-1, conv1-3 owned +-2, up1
+// owned +-3 (16 x 8 input blocks = 32 x 16 output pixels)
+static OwnedBlocks chain_owned(const TileGrid& g, int li) {
+  return li == 22 ? owned_blocks(g, 0, 16, 16) : li == 21 ? owned_blocks(g, 1, 16, 16)
+       : li == 20 ? owned_blocks(g, 2, 16, 16) : owned_blocks(g, 3, 32, 16);
+}
+
+// Work lists of the level-0 decoder chain for one image shape (conv_tc.cuh): per layer the needed items of ALL the
+// image's tiles in launch order, plus where each tile's entries start, so that a sub-batch [t0, t1) of tiles uses the
+// slice [off[t0], off[t1]) with the item indices rebased to its first tile.  Kept on the device until the shape changes.
+struct WorkLists {
+  int h = 0, w = 0;
+  int* d[4] = {nullptr, nullptr, nullptr, nullptr};     // layers 19..22
+  std::vector<int> off[4];                              // per layer: n_tiles + 1 offsets
+  std::vector<int> host[4];
+};
+
+static int build_work_lists(ecseg_ctx* ctx, WorkLists& wl, const TileGrid& g, cudaStream_t st) {
+  if (wl.h == g.h && wl.w == g.w) return ECSEG_OK;
+  ECSEG_CUDA(cudaStreamSynchronize(st));                 // (a previous image of another shape may still read the old lists)
+  for (int k = 0; k < 4; ++k) {
+    const int li = 19 + k;
+    const LayerDef& l = kLayers[li];
+    const int out_hw = kTile >> l.level, in_hw = l.convT ? out_hw / 2 : out_hw;
+    const int bcols = in_hw / (l.convT ? 8 : 16), brows = in_hw / 16;
+    const OwnedBlocks ob = chain_owned(g, li);
+    if (!ob.on) { wl.h = 0; wl.w = 0; return ECSEG_E_STATE; }      // (caller falls back to computing everything)
+    std::vector<int>& v = wl.host[k];
+    v.clear();
+    wl.off[k].assign(g.n() + 1, 0);
+    for (int t = 0; t < g.n(); ++t) {
+      wl.off[k][t] = (int)v.size();
+      for (int by = 0; by < brows; ++by) {
+        if (li == 22) {                                   // head: one block per entry, index = position in the launch
+          for (int bx = 0; bx < bcols; ++bx)
+            if (ob.needed(t, by, bx)) v.push_back((t * brows + by) * bcols + bx);
+          continue;
+        }
+        for (int bp = 0; bp < bcols; bp += 2) {           // CTA pairs over the owned_col order
+          const int keep = (ob.needed(t, by, owned_col(bp, bcols)) ? 1 : 0) | (ob.needed(t, by, owned_col(bp + 1, bcols)) ? 2 : 0);
+          if (keep) v.push_back((((t * brows + by) * bcols + bp) >> 1) | (keep << 28));
+        }
+      }
+    }
+    wl.off[k][g.n()] = (int)v.size();
+    if (wl.d[k]) { cudaFree(wl.d[k]); wl.d[k] = nullptr; }
+    ECSEG_CUDA(cudaMalloc(&wl.d[k], std::max<size_t>(v.size(), 1) * sizeof(int)));
+    ECSEG_CUDA(cudaMemcpy(wl.d[k], v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  wl.h = g.h; wl.w = g.w;
+  return ECSEG_OK;
+}
+
+static WorkLists* new_work_lists() { return new WorkLists(); }
+static void free_work_lists(WorkLists* wl) {
+  if (!wl) return;
+  for (auto& d : wl->d) if (d) cudaFree(d);
+  delete wl;
+}
+
+// FLOPs of one image's U-Net: `ref` = what model.predict_on_batch does for every tile in full (SURVEY Appendix C, 2 FLOP
+// per MAC), `exec` = what the labels-only path issues to the tensor cores once the blocks in the unowned margin of the
+// level-0 decoder chain are skipped (a CTA pair runs both of its blocks when either is needed).
+int unet_work(int h, int w, int skip_unowned, double* ref, double* exec) {
+  if (h < kTile || w < kTile) return ECSEG_E_INVALID;
+  const TileGrid g = make_grid(h, w);
+  double r = 0.0, e = 0.0;
+  for (int li = 0; li < 23; ++li) {
+    const LayerDef& l = kLayers[li];
+    const int out_hw = kTile >> l.level, in_hw = l.convT ? out_hw / 2 : out_hw;
+    const double per_px = 2.0 * 9.0 * l.cin * l.cout;                 // per pixel of the grid the GEMM's M dimension tiles
+    const double full = per_px * in_hw * in_hw * g.n();
+    r += full;
+    if (!skip_unowned || li < 19) { e += full; continue; }
+    const int bw_px = l.convT ? 8 : 16, bcols = in_hw / bw_px, brows = in_hw / 16;
+    const OwnedBlocks ob = chain_owned(g, li);
+    if (!ob.on) { e += full; continue; }
+    long long blocks = 0;
+    for (int t = 0; t < g.n(); ++t)
+      for (int by = 0; by < brows; ++by) {
+        if (li == 22) { for (int bx = 0; bx < bcols; ++bx) blocks += ob.needed(t, by, bx); continue; }
+        for (int bp = 0; bp < bcols; bp += 2)      // CTA pairs over the owned_col order
+          blocks += 2 * (ob.needed(t, by, owned_col(bp, bcols)) || ob.needed(t, by, owned_col(bp + 1, bcols)));
+      }
+    e += per_px * 16.0 * bw_px * blocks;
+  }
+  if (ref) *ref = r;
+  if (exec) *exec = e;
+  return ECSEG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -570,6 +708,10 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   const Wire& wr = kWires[li];
   const bool bf16 = net->precision == ECSEG_PREC_BF16;
   const int NT = ctx->max_tiles - tile0;      // tiles addressable behind the offset base pointers
+  // Labels-only path (ecseg_segment_image*): nobody sees a tile's prediction outside the region the stitcher takes from
+  // it, so the last layers skip the blocks that lie in the 25-px overlap margin (conv_tc.cuh OwnedBlocks): the head
+  // computes owned pixels, conv1-4 owned +-1, conv1-3 owned +-2, up1 owned +-3.
+  const bool skip_unowned = net->skip_unowned && d_labels && grid && !d_probs && !d_logits && li >= 19;
   auto tile_base = [&](int buf, int hw) -> char* {    // first byte of tile `tile0` in activation buffer `buf`
     return (char*)net->buf[buf] + (size_t)tile0 * hw * hw * kBufs[buf].ch * 2;
   };
@@ -585,6 +727,15 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
     if (grid) h.grid = *grid;
     h.device_error = &ctx->counters->device_error;
     h.range_error = &ctx->counters->range_error;
+    if (skip_unowned) {
+      const int rc = build_work_lists(ctx, *net->work_lists, *grid, st);
+      if (rc == ECSEG_OK) {
+        const std::vector<int>& off = net->work_lists->off[3];
+        if (off[tile0 + n] == off[tile0]) return ECSEG_OK;       // no owned pixel in these tiles
+        h.work = net->work_lists->d[3] + off[tile0]; h.n_work = off[tile0 + n] - off[tile0];
+        h.work_base = tile0 * (kTile / 16) * (kTile / 16);
+      } else if (rc != ECSEG_E_STATE) return rc;
+    }
     return head_tc_launch(ctx, h, st);
   }
   ConvTcParams p;
@@ -649,6 +800,15 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   p.cin_chunks = l.cin / 64; p.n_chunks = rows / n_tile; p.cout_rows = rows;
   p.out_choff = wr.choff;
   p.bias = net->b[li]; p.relu = l.relu; p.is_bf16 = bf16;
+  if (skip_unowned) {
+    const int rc = build_work_lists(ctx, *net->work_lists, *grid, st);
+    if (rc == ECSEG_OK) {
+      const std::vector<int>& off = net->work_lists->off[li - 19];
+      if (off[tile0 + n] == off[tile0]) return ECSEG_OK;         // nothing downstream reads these tiles' blocks
+      p.work = net->work_lists->d[li - 19] + off[tile0]; p.n_work = off[tile0 + n] - off[tile0];
+      p.work_base = tile0 * ((in_hw / 16) * (in_hw / (l.convT ? 8 : 16)) / 2);   // pair items per tile
+    } else if (rc != ECSEG_E_STATE) return rc;
+  }
   p.device_error = &ctx->counters->device_error;
   p.act_overflow = &ctx->counters->act_overflow;
   p.layer_id = li + 1;

@@ -27,6 +27,15 @@ def tile_grid(h: int, w: int):
     return pos, nr.value, nc.value
 
 
+def unet_work(h: int, w: int, labels_only: bool = True):
+    """(reference FLOPs, executed FLOPs) of one h x w image's U-Net (ecseg_unet_work): the whole-image calls skip the
+    blocks of the last four layers that lie in the part of a tile the stitcher never takes."""
+    ref, ex = ctypes.c_double(), ctypes.c_double()
+    if _lib.load().ecseg_unet_work(h, w, 1 if labels_only else 0, byref(ref), byref(ex)) != 0:
+        raise ValueError("images smaller than 256x256 cannot be tiled (reference limitation)")
+    return ref.value, ex.value
+
+
 class Engine:
     def __init__(self, device: int = 0, max_h: int = 2048, max_w: int = 2048, max_tiles: int | None = None):
         if not torch.cuda.is_available():

@@ -230,6 +230,14 @@ int ecseg_device_error(ecseg_ctx* ctx, int* code);
  * from their _wait.  conv1-1, whose input is bounded (0..255), is checked once at ecseg_load_weights instead. */
 int ecseg_activation_overflow(ecseg_ctx* ctx, int* layer);
 
+/* Work accounting of the U-Net for one h x w image (host only).  *flops_reference = what model.predict_on_batch
+ * (src/utils.py:115) computes: every tile in full, 2 FLOP per multiply-add (97.014 GFLOP per tile).  *flops_executed =
+ * what the library issues: equal to the reference for the staged calls (labels_only == 0); for the whole-image calls
+ * (labels_only != 0), whose only U-Net output is the stitched label map, the last four layers skip the 16x16 blocks
+ * that lie entirely in the part of a tile the stitcher (src/image_tools.py:188-252) never takes -- the tiles overlap
+ * by 25 px and a tile contributes about 206 x 206 of its 256 x 256 prediction; the result is bit-identical. */
+int ecseg_unet_work(int h, int w, int labels_only, double* flops_reference, double* flops_executed);
+
 /* Number of kernels this library launched on behalf of ctx since creation. */
 int64_t ecseg_launch_count(ecseg_ctx* ctx);
 
