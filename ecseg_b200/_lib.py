@@ -62,6 +62,7 @@ SIGNATURES = {
     "ecseg_debug_trace": (c_int, [c_void_p, c_void_p, c_int]),
     "ecseg_device_error": (c_int, [c_void_p, POINTER(c_int)]),
     "ecseg_activation_overflow": (c_int, [c_void_p, POINTER(c_int)]),
+    "ecseg_debug_owned_blocks": (c_int, [c_int, c_int, c_int, c_void_p, POINTER(c_int), POINTER(c_int)]),
     "ecseg_unet_work": (c_int, [c_int, c_int, c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double)]),
     "ecseg_launch_count": (c_int64, [c_void_p]),
     "ecseg_last_stage_ms": (c_int, [c_void_p, POINTER(c_float)]),

@@ -486,6 +486,10 @@ int ecseg_unet_work(int h, int w, int labels_only, double* flops_reference, doub
   return unet_work(h, w, labels_only && !no_skip, flops_reference, flops_executed);
 }
 
+int ecseg_debug_owned_blocks(int h, int w, int layer, uint8_t* mask, int* block_rows, int* block_cols) {
+  return unet_owned_mask(h, w, layer, mask, block_rows, block_cols);
+}
+
 int ecseg_last_stage_ms(ecseg_ctx* ctx, float ms[4]) {
   API_GUARD(ctx);
   if (!ctx->ev_valid || !ms) { if (ctx) ctx->err = "last_stage_ms: no segment_image call yet"; return ECSEG_E_STATE; }

@@ -208,5 +208,6 @@ int unet_forward(ecseg_ctx* ctx, const uint8_t* d_tiles, const uint8_t* d_pre, c
                  float* d_probs, float* d_logits, uint8_t* d_labels, cudaStream_t st);
 int unet_debug_layer(ecseg_ctx* ctx, int layer, int n, float* d_out, cudaStream_t st);
 int unet_work(int h, int w, int skip_unowned, double* ref, double* exec);
+int unet_owned_mask(int h, int w, int layer, uint8_t* mask, int* rows, int* cols);
 
 }  // namespace ecseg

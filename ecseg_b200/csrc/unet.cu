@@ -607,6 +607,23 @@ static int build_work_lists(ecseg_ctx* ctx, WorkLists& wl, const TileGrid& g, cu
   return ECSEG_OK;
 }
 
+// needed-block mask of one chain layer (19..22) for an h x w image: mask[tile][block row][block col] (host only; tests)
+int unet_owned_mask(int h, int w, int layer, uint8_t* mask, int* rows, int* cols) {
+  if (h < kTile || w < kTile || layer < 19 || layer > 22) return ECSEG_E_INVALID;
+  const TileGrid g = make_grid(h, w);
+  const LayerDef& l = kLayers[layer];
+  const int out_hw = kTile >> l.level, in_hw = l.convT ? out_hw / 2 : out_hw;
+  const int bcols = in_hw / (l.convT ? 8 : 16), brows = in_hw / 16;
+  if (rows) *rows = brows;
+  if (cols) *cols = bcols;
+  const OwnedBlocks ob = chain_owned(g, layer);
+  if (mask)
+    for (int t = 0; t < g.n(); ++t)
+      for (int by = 0; by < brows; ++by)
+        for (int bx = 0; bx < bcols; ++bx) mask[((size_t)t * brows + by) * bcols + bx] = ob.on ? ob.needed(t, by, bx) : 1;
+  return ECSEG_OK;
+}
+
 static WorkLists* new_work_lists() { return new WorkLists(); }
 static void free_work_lists(WorkLists* wl) {
   if (!wl) return;

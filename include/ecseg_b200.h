@@ -238,6 +238,12 @@ int ecseg_activation_overflow(ecseg_ctx* ctx, int* layer);
  * by 25 px and a tile contributes about 206 x 206 of its 256 x 256 prediction; the result is bit-identical. */
 int ecseg_unet_work(int h, int w, int labels_only, double* flops_reference, double* flops_executed);
 
+/* Which blocks of U-Net layer `layer` (19 up1, 20 conv1-3, 21 conv1-4, 22 head; ecseg_b200.spec.UNET_LAYERS) the
+ * whole-image calls compute for an h x w image: mask[tile][block_row][block_col] (1 = computed), blocks being 16 x 16
+ * pixels of the layer's input grid (16 x 8 for up1).  mask == NULL only returns the block grid.  Host only; lets a
+ * test check the skipping against the stitcher's ownership map (src/image_tools.py:188-252) without a GPU. */
+int ecseg_debug_owned_blocks(int h, int w, int layer, uint8_t* mask, int* block_rows, int* block_cols);
+
 /* Number of kernels this library launched on behalf of ctx since creation. */
 int64_t ecseg_launch_count(ecseg_ctx* ctx);
 
