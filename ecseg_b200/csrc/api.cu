@@ -7,6 +7,8 @@
 #include <mutex>
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX 3: ranges cost nothing unless a tool (nsys / ncu --nvtx) is attached
+
 #include "artifacts_host.h"
 #include "common.cuh"
 
@@ -250,16 +252,22 @@ int ecseg_segment_image(ecseg_ctx* ctx, const void* d_img, int h, int w, int ch,
   if (h < kTile || w < kTile) { ctx->err = "ecseg_segment_image: need h,w >= 256"; return ECSEG_E_INVALID; }
   TileGrid g = make_grid(h, w);
   if (g.n() > ctx->max_tiles) { ctx->err = "ecseg_segment_image: tile count exceeds the context's max_tiles"; return ECSEG_E_INVALID; }
+  // NVTX ranges mark the host-side enqueue of each stage (the stages themselves are timed with the CUDA events)
+  struct Range { explicit Range(const char* n) { nvtxRangePushA(n); } ~Range() { nvtxRangePop(); } };
+  Range whole("ecseg_segment_image");
   ECSEG_CUDA(cudaEventRecord(ctx->ev[0], st));
-  ECSEG_TRY(fe_preprocess(ctx, d_img, h, w, ch, bytes_per_sample, ctx->pre, d_dapi, st));
+  { Range r("ecseg:preprocess"); ECSEG_TRY(fe_preprocess(ctx, d_img, h, w, ch, bytes_per_sample, ctx->pre, d_dapi, st)); }
   ECSEG_CUDA(cudaEventRecord(ctx->ev[1], st));
   // tiles are gathered inside conv1-1, the stitch is fused into the head's epilogue
-  ECSEG_TRY(unet_turnstile(ctx, st, true));
-  ECSEG_TRY(unet_forward(ctx, nullptr, ctx->pre, &g, g.n(), nullptr, nullptr, d_labels, st));
-  ECSEG_TRY(unet_turnstile(ctx, st, false));
+  {
+    Range r("ecseg:unet");
+    ECSEG_TRY(unet_turnstile(ctx, st, true));
+    ECSEG_TRY(unet_forward(ctx, nullptr, ctx->pre, &g, g.n(), nullptr, nullptr, d_labels, st));
+    ECSEG_TRY(unet_turnstile(ctx, st, false));
+  }
   ECSEG_CUDA(cudaEventRecord(ctx->ev[2], st));
   ECSEG_CUDA(cudaEventRecord(ctx->ev[3], st));
-  ECSEG_TRY(pp_postprocess(ctx, d_labels, h, w, flags, d_n_ec, d_ec_px, st));
+  { Range r("ecseg:postprocess"); ECSEG_TRY(pp_postprocess(ctx, d_labels, h, w, flags, d_n_ec, d_ec_px, st)); }
   ECSEG_CUDA(cudaEventRecord(ctx->ev[4], st));
   ctx->ev_valid = true;
   return ECSEG_OK;
