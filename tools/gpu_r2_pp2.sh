@@ -1,9 +1,9 @@
 #!/bin/bash
-# post-processing: parity tests, then same-box A/B: fused rule passes / ticket-fused border unions vs the round-1 shape
+# post-processing: parity tests in both shapes, then same-box A/B of the fused rule passes (ECSEG_PP_UNFUSED=1 = round-1 shape)
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests/test_gpu_postproc.py tests/test_gpu_frontend.py tests/test_gpu_overlay.py tests/test_gpu_example.py -m gpu -x -q > gpurun_out/pytest_pp2.txt 2>&1; echo "pytest rc=$?"
 tail -5 gpurun_out/pytest_pp2.txt
-ECSEG_PP_SEPARATE_BORDER=1 ECSEG_PP_UNFUSED=1 timeout 900 python -m pytest tests/test_gpu_postproc.py -m gpu -x -q > gpurun_out/pytest_pp2_old.txt 2>&1; echo "pytest (old shape) rc=$?"
+ECSEG_PP_UNFUSED=1 timeout 900 python -m pytest tests/test_gpu_postproc.py -m gpu -x -q > gpurun_out/pytest_pp2_old.txt 2>&1; echo "pytest (unfused) rc=$?"
 tail -2 gpurun_out/pytest_pp2_old.txt
 line() {
 python - "$1" "$2" <<'PY'
@@ -15,9 +15,7 @@ PY
 }
 PP="python bench.py --workload postproc --steps 16 --no-cpu-baseline"
 for rep in 1 2; do
-  timeout 300 $PP > gpurun_out/pp2_new_$rep.json 2> gpurun_out/pp2.err; line gpurun_out/pp2_new_$rep.json "tickets + fused rules rep $rep"
-  ECSEG_PP_SEPARATE_BORDER=1 timeout 300 $PP > gpurun_out/pp2_sepb_$rep.json 2>> gpurun_out/pp2.err; line gpurun_out/pp2_sepb_$rep.json "separate border launch, fused rules rep $rep"
-  ECSEG_PP_UNFUSED=1 timeout 300 $PP > gpurun_out/pp2_unf_$rep.json 2>> gpurun_out/pp2.err; line gpurun_out/pp2_unf_$rep.json "tickets, unfused rules rep $rep"
-  ECSEG_PP_SEPARATE_BORDER=1 ECSEG_PP_UNFUSED=1 timeout 300 $PP > gpurun_out/pp2_old_$rep.json 2>> gpurun_out/pp2.err; line gpurun_out/pp2_old_$rep.json "round-1 shape (separate border, unfused) rep $rep"
+  timeout 300 $PP > gpurun_out/pp2_new_$rep.json 2> gpurun_out/pp2.err; line gpurun_out/pp2_new_$rep.json "fused rule passes rep $rep"
+  ECSEG_PP_UNFUSED=1 timeout 300 $PP > gpurun_out/pp2_unf_$rep.json 2>> gpurun_out/pp2.err; line gpurun_out/pp2_unf_$rep.json "rules as own passes rep $rep"
 done
 tail -3 gpurun_out/pp2.err
