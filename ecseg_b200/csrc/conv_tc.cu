@@ -28,6 +28,9 @@
 //                   two warp shuffles and stored the same way.
 //   warps 12..15  : (fused first layer only) conv1-1 generator, see FUSE1 below.
 // Pipelines are mbarrier based (full/empty per A stage, per B stage, per accumulator stage).
+// A launch walks either every (M block, N chunk) item round-robin or a host-built WORK LIST of the items that matter
+// (conv_tc.cuh: the whole-image path drops the blocks that lie in the part of a tile the stitcher never takes); every
+// epilogue also tracks the largest 16-bit pattern it stores (the fp16 range guard, ecseg_activation_overflow).
 #include "conv_tc.cuh"
 #include "tc_common.cuh"
 

@@ -1025,7 +1025,7 @@ void pp_free_graphs(ecseg_ctx* ctx) {
   ctx->pp_graphs.clear();
 }
 
-// The 24 launches of one label map are small (4-47 us) and strictly dependent: issued one by one, the stage is bound by
+// The ~21 launches of one label map are small (4-47 us) and strictly dependent: issued one by one, the stage is bound by
 // launch latency, not by HBM.  The sequence depends only on the arguments (pointers, shape, flags, labelling parity),
 // never on the data, so it is captured once per distinct argument set into a CUDA graph and replayed: one graph
 // launch per map, the dependent kernels chained on the device.  ECSEG_PP_NO_GRAPH=1 (or the legacy default stream,

@@ -4,6 +4,9 @@
 // topology template src/model_layers/models.py:17-136 with 1 input channel, 4 classes, softmax
 // (ecseg_b200/spec.py holds the same table).
 //
+// The whole-image calls (labels only) run the last four layers over work lists of the blocks the reference's stitcher
+// can take from each tile (ownership-aware skipping, below); the staged calls compute every tile in full.
+//
 // Two arithmetic modes share the schedule:
 //   * fp32  : CUDA-core FMA direct convolution (k_conv_fp32) -- parity mode.
 //   * bf16 / fp16 : tcgen05 implicit GEMM (conv_tc.cu) -- throughput mode.
