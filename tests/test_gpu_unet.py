@@ -171,3 +171,29 @@ def test_fused_first_layer_pair_equals_single_cta(monkeypatch):
                 assert torch.equal(a, b)
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("shape", [(256, 256), (256, 700), (700, 512), (300, 300), (513, 777), (462, 1100), (1040, 600)])
+def test_owned_block_skipping_equals_full_computation(shape):
+    """The whole-image call computes only the blocks of the last four layers that the stitcher can take from a tile
+    (work lists, unet.cu); the staged calls compute every tile in full.  Same labels, bit for bit, on tile grids with a
+    single row / column, pulled-back last tiles and tiles that own only a sliver."""
+    from ecseg_b200 import synth, weights as wmod
+    from ecseg_b200.engine import Engine, unet_work
+    h, w = shape
+    img = synth.synth_dapi(90 + h % 7 + w % 5, h, w)
+    eng = Engine(0, max(h, 256), max(w, 256))
+    try:
+        eng.load_weights(wmod.make_weights(0), "fp16")
+        for rep in range(2):                                   # second pass: buffers hold the first pass's stale margins
+            labels, n_ec, ec_px = eng.segment_host(img)
+            pre, _ = eng.preprocess(img)
+            raw = eng.stitch_argmax(eng.unet_forward(eng.tile(pre)), h, w)
+            want, n2, px2 = eng.postprocess(raw)
+            assert np.array_equal(labels, want.cpu().numpy()), (shape, rep)
+            assert (n_ec, ec_px) == (n2, px2)
+            assert eng.activation_overflow() == -1
+        ref, ex = unet_work(h, w)
+        assert ex <= ref and (ex < ref or shape == (256, 256))
+    finally:
+        eng.close()
