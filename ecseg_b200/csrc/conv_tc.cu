@@ -767,7 +767,7 @@ int launch_impl(ecseg_ctx* ctx, ConvTcParams& p, cudaStream_t st) {
   }
   const int n_mblocks = p.n_img * (p.H >> 4) * (p.W / blk_w(NACC));
   const int n_items = p.work ? p.n_work : ((n_mblocks + CS - 1) / CS) * p.n_chunks;
-  if (p.work && (FUSE1 || p.n_chunks != 1 || p.n_work < 1)) { ctx->err = "conv_tc: a work list needs a plain single-chunk layer"; return ECSEG_E_INVALID; }
+  if (p.work && (FUSE1 || p.n_work < 1 || (p.n_chunks != 1 && p.work_base != 0))) { ctx->err = "conv_tc: bad work list"; return ECSEG_E_INVALID; }
   int clusters = ctx->n_sms / CS;
   if (n_items < clusters) clusters = n_items;
   cudaLaunchConfig_t cfg = {};

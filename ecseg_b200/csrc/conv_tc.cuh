@@ -14,7 +14,8 @@ constexpr int kMaxGridAxis = 40;   // tile rows / columns an OwnedBlocks table c
 // (its "owned" region, image_tools.py:188-252 / stitch.cuh axis_owner) matter downstream.  The 256x256 tiles overlap by
 // 25 px and a tile owns only ~206x206 of its own prediction; the last layers of the network have a receptive field of a
 // few pixels, so their blocks that lie entirely in the unowned margin are dead work: the head needs conv1-4 only on
-// owned +-1 px, conv1-4 needs conv1-3 on owned +-2, conv1-3 needs up1 on owned +-3.  Per tile row index ri (column
+// owned +-1 px, conv1-4 needs conv1-3 on owned +-2, conv1-3 needs up1 on owned +-3 (and so on into decoder level 1, where
+// it only bites for tiles that own a strip: unet.cu needed_range).  Per tile row index ri (column
 // index ci) of the image's tile grid: the half-open range of needed block rows (columns), in the layer's own block units.
 // (host side: unet.cu builds a compact WORK LIST of the needed items from it, so that the persistent CTAs share the
 //  remaining work evenly and test nothing per item)

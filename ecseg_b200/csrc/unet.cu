@@ -537,19 +537,51 @@ static void owned_range(int len, int n, int rem, int i, int& lo, int& hi) {
   if (hi <= lo) { lo = 0; hi = 0; }
 }
 
-// Blocks of `bs_r` x `bs_c` OUTPUT pixels a layer must compute so that its output is valid on owned +- margin.
-static OwnedBlocks owned_blocks(const TileGrid& g, int margin, int bs_r, int bs_c) {
+// The listed layers: the last seven of the network (decoder levels 1 and 0).  Going backwards from the pixels the
+// stitcher takes from a tile ("owned", [lo, hi) per axis), each layer's output has to be valid on
+//   22 head      owned                      21 conv1-4   owned +-1           20 conv1-3   owned +-2
+//   19 up1       owned +-3 =: [a0, b0)      (256-px grid; its blocks are 16 x 8 input = 32 x 16 output pixels)
+//   18 conv2-4   R1 = { i : {2i, 2i+1, 2i+2} meets [a0, b0) }   (128-px grid: out[2i + k] += in[i] * K[k], k = 0..2)
+//   17 conv2-3   R1 +-1                     16 up2       R1 +-2   (blocks 32 x 16 output pixels)
+// Deeper layers are needed in full (at 64 px the range already covers the tile).  For an interior tile of a large
+// image level 1 keeps every block too; it pays on the tiles next to a pulled-back last tile, which own only a strip.
+constexpr int kFirstListed = 16, kNumListed = 7;
+
+static void needed_range(int li, int lo, int hi, int& a, int& b, int& size) {
+  auto clip = [](int& x, int& y, int n) { x = std::max(0, x); y = std::min(n, y); };
+  if (li >= 19) {
+    const int m = 22 - li;
+    a = lo - m; b = hi + m; size = kTile;
+    clip(a, b, size);
+    return;
+  }
+  int a0 = lo - 3, b0 = hi + 3;
+  clip(a0, b0, kTile);
+  size = kTile / 2;
+  a = (std::max(0, a0 - 2) + 1) / 2;       // smallest i with 2i + 2 >= a0
+  b = (b0 - 1) / 2 + 1;                    // one past the largest i with 2i <= b0 - 1
+  const int m = 18 - li;
+  a -= m; b += m;
+  clip(a, b, size);
+}
+
+// Blocks a listed layer must compute, per tile row / column of the grid, in the layer's own block units.
+static OwnedBlocks chain_owned(const TileGrid& g, int li) {
   OwnedBlocks ob;
   memset(&ob, 0, sizeof(ob));
-  if (g.nr > kMaxGridAxis || g.nc > kMaxGridAxis) return ob;      // (on == 0: compute everything)
+  if (g.nr > kMaxGridAxis || g.nc > kMaxGridAxis || li < kFirstListed || li > 22) return ob;      // (on == 0: compute everything)
   ob.on = 1; ob.nr = g.nr;
+  const bool convT = kLayers[li].convT != 0;
+  const int bs_r = convT ? 32 : 16, bs_c = 16;       // block size in OUTPUT pixels (a transposed conv's 16 x 8 input block)
   auto fill = [&](int len, int n, int rem, int bs, unsigned char* blo, unsigned char* bhi) {
     for (int i = 0; i < n; ++i) {
-      int lo, hi;
+      int lo, hi, a, b, size;
       owned_range(len, n, rem, i, lo, hi);
       if (hi <= lo) { blo[i] = 0; bhi[i] = 0; continue; }
-      blo[i] = (unsigned char)(std::max(0, lo - margin) / bs);
-      bhi[i] = (unsigned char)((std::min(kTile, hi + margin) - 1) / bs + 1);
+      needed_range(li, lo, hi, a, b, size);
+      if (b <= a) { blo[i] = 0; bhi[i] = 0; continue; }
+      blo[i] = (unsigned char)(a / bs);
+      bhi[i] = (unsigned char)((b - 1) / bs + 1);
     }
   };
   fill(g.h, g.nr, g.rem_r, bs_r, ob.r_lo, ob.r_hi);
@@ -557,31 +589,27 @@ static OwnedBlocks owned_blocks(const TileGrid& g, int margin, int bs_r, int bs_
   return ob;
 }
 
-// margins of the level-0 decoder chain: the head computes owned pixels, conv1-4 owned +-1, conv1-3 owned +-2, up1
-// owned +-3 (16 x 8 input blocks = 32 x 16 output pixels)
-static OwnedBlocks chain_owned(const TileGrid& g, int li) {
-  return li == 22 ? owned_blocks(g, 0, 16, 16) : li == 21 ? owned_blocks(g, 1, 16, 16)
-       : li == 20 ? owned_blocks(g, 2, 16, 16) : owned_blocks(g, 3, 32, 16);
-}
-
-// Work lists of the level-0 decoder chain for one image shape (conv_tc.cuh): per layer the needed items of ALL the
-// image's tiles in launch order, plus where each tile's entries start, so that a sub-batch [t0, t1) of tiles uses the
-// slice [off[t0], off[t1]) with the item indices rebased to its first tile.  Kept on the device until the shape changes.
+// Work lists of the listed layers for one image shape (conv_tc.cuh): per layer the needed items of ALL the image's
+// tiles in launch order, plus where each tile's entries start, so that a sub-batch [t0, t1) of tiles (level-0 chain
+// only) uses the slice [off[t0], off[t1]) with the item indices rebased to its first tile.  A layer with several
+// output-channel chunks (up2) lists chunk 0's items for every tile, then chunk 1's: it is never sub-batched.  Kept on
+// the device until the shape changes.
 struct WorkLists {
   int h = 0, w = 0;
-  int* d[4] = {nullptr, nullptr, nullptr, nullptr};     // layers 19..22
-  std::vector<int> off[4];                              // per layer: n_tiles + 1 offsets
-  std::vector<int> host[4];
+  int* d[kNumListed] = {};                              // layers kFirstListed .. 22
+  std::vector<int> off[kNumListed];                     // per layer: n_tiles + 1 offsets (single-chunk layers)
+  std::vector<int> host[kNumListed];
 };
 
 static int build_work_lists(ecseg_ctx* ctx, WorkLists& wl, const TileGrid& g, cudaStream_t st) {
   if (wl.h == g.h && wl.w == g.w) return ECSEG_OK;
   ECSEG_CUDA(cudaStreamSynchronize(st));                 // (a previous image of another shape may still read the old lists)
-  for (int k = 0; k < 4; ++k) {
-    const int li = 19 + k;
+  for (int k = 0; k < kNumListed; ++k) {
+    const int li = kFirstListed + k;
     const LayerDef& l = kLayers[li];
     const int out_hw = kTile >> l.level, in_hw = l.convT ? out_hw / 2 : out_hw;
     const int bcols = in_hw / (l.convT ? 8 : 16), brows = in_hw / 16;
+    const int n_chunks = l.convT ? l.cout / 64 : (l.cout + 127) / 128;      // (the variant table of run_layer_tc)
     const OwnedBlocks ob = chain_owned(g, li);
     if (!ob.on) { wl.h = 0; wl.w = 0; return ECSEG_E_STATE; }      // (caller falls back to computing everything)
     std::vector<int>& v = wl.host[k];
@@ -602,6 +630,14 @@ static int build_work_lists(ecseg_ctx* ctx, WorkLists& wl, const TileGrid& g, cu
       }
     }
     wl.off[k][g.n()] = (int)v.size();
+    if (n_chunks > 1) {          // item = chunk * (pair items of the launch) + pair item
+      const size_t per_chunk = v.size();
+      const int n_mgroups = g.n() * brows * bcols / 2;
+      for (int c = 1; c < n_chunks; ++c)
+        for (size_t e = 0; e < per_chunk; ++e) v.push_back(((v[e] & kWorkItemMask) + c * n_mgroups) | (v[e] & ~kWorkItemMask));
+      wl.off[k].assign(g.n() + 1, -1);      // not sliceable by tile
+      wl.off[k][0] = 0; wl.off[k][g.n()] = (int)v.size();
+    }
     if (wl.d[k]) { cudaFree(wl.d[k]); wl.d[k] = nullptr; }
     ECSEG_CUDA(cudaMalloc(&wl.d[k], std::max<size_t>(v.size(), 1) * sizeof(int)));
     ECSEG_CUDA(cudaMemcpy(wl.d[k], v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -612,7 +648,7 @@ static int build_work_lists(ecseg_ctx* ctx, WorkLists& wl, const TileGrid& g, cu
 
 // needed-block mask of one chain layer (19..22) for an h x w image: mask[tile][block row][block col] (host only; tests)
 int unet_owned_mask(int h, int w, int layer, uint8_t* mask, int* rows, int* cols) {
-  if (h < kTile || w < kTile || layer < 19 || layer > 22) return ECSEG_E_INVALID;
+  if (h < kTile || w < kTile || layer < kFirstListed || layer > 22) return ECSEG_E_INVALID;
   const TileGrid g = make_grid(h, w);
   const LayerDef& l = kLayers[layer];
   const int out_hw = kTile >> l.level, in_hw = l.convT ? out_hw / 2 : out_hw;
@@ -647,7 +683,7 @@ int unet_work(int h, int w, int skip_unowned, double* ref, double* exec) {
     const double per_px = 2.0 * 9.0 * l.cin * l.cout;                 // per pixel of the grid the GEMM's M dimension tiles
     const double full = per_px * in_hw * in_hw * g.n();
     r += full;
-    if (!skip_unowned || li < 19) { e += full; continue; }
+    if (!skip_unowned || li < kFirstListed) { e += full; continue; }
     const int bw_px = l.convT ? 8 : 16, bcols = in_hw / bw_px, brows = in_hw / 16;
     const OwnedBlocks ob = chain_owned(g, li);
     if (!ob.on) { e += full; continue; }
@@ -731,7 +767,7 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   // Labels-only path (ecseg_segment_image*): nobody sees a tile's prediction outside the region the stitcher takes from
   // it, so the last layers skip the blocks that lie in the 25-px overlap margin (conv_tc.cuh OwnedBlocks): the head
   // computes owned pixels, conv1-4 owned +-1, conv1-3 owned +-2, up1 owned +-3.
-  const bool skip_unowned = net->skip_unowned && d_labels && grid && !d_probs && !d_logits && li >= 19;
+  const bool skip_unowned = net->skip_unowned && d_labels && grid && !d_probs && !d_logits && li >= kFirstListed;
   auto tile_base = [&](int buf, int hw) -> char* {    // first byte of tile `tile0` in activation buffer `buf`
     return (char*)net->buf[buf] + (size_t)tile0 * hw * hw * kBufs[buf].ch * 2;
   };
@@ -750,9 +786,9 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
     if (skip_unowned) {
       const int rc = build_work_lists(ctx, *net->work_lists, *grid, st);
       if (rc == ECSEG_OK) {
-        const std::vector<int>& off = net->work_lists->off[3];
+        const std::vector<int>& off = net->work_lists->off[22 - kFirstListed];
         if (off[tile0 + n] == off[tile0]) return ECSEG_OK;       // no owned pixel in these tiles
-        h.work = net->work_lists->d[3] + off[tile0]; h.n_work = off[tile0 + n] - off[tile0];
+        h.work = net->work_lists->d[22 - kFirstListed] + off[tile0]; h.n_work = off[tile0 + n] - off[tile0];
         h.work_base = tile0 * (kTile / 16) * (kTile / 16);
       } else if (rc != ECSEG_E_STATE) return rc;
     }
@@ -823,9 +859,10 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   if (skip_unowned) {
     const int rc = build_work_lists(ctx, *net->work_lists, *grid, st);
     if (rc == ECSEG_OK) {
-      const std::vector<int>& off = net->work_lists->off[li - 19];
+      const std::vector<int>& off = net->work_lists->off[li - kFirstListed];
+      if (off[tile0] < 0 || off[tile0 + n] < 0) { ctx->err = "unet: a multi-chunk work list cannot be sliced by tile"; return ECSEG_E_STATE; }
       if (off[tile0 + n] == off[tile0]) return ECSEG_OK;         // nothing downstream reads these tiles' blocks
-      p.work = net->work_lists->d[li - 19] + off[tile0]; p.n_work = off[tile0 + n] - off[tile0];
+      p.work = net->work_lists->d[li - kFirstListed] + off[tile0]; p.n_work = off[tile0 + n] - off[tile0];
       p.work_base = tile0 * ((in_hw / 16) * (in_hw / (l.convT ? 8 : 16)) / 2);   // pair items per tile
     } else if (rc != ECSEG_E_STATE) return rc;
   }

@@ -233,12 +233,14 @@ int ecseg_activation_overflow(ecseg_ctx* ctx, int* layer);
 /* Work accounting of the U-Net for one h x w image (host only).  *flops_reference = what model.predict_on_batch
  * (src/utils.py:115) computes: every tile in full, 2 FLOP per multiply-add (97.014 GFLOP per tile).  *flops_executed =
  * what the library issues: equal to the reference for the staged calls (labels_only == 0); for the whole-image calls
- * (labels_only != 0), whose only U-Net output is the stitched label map, the last four layers skip the 16x16 blocks
- * that lie entirely in the part of a tile the stitcher (src/image_tools.py:188-252) never takes -- the tiles overlap
- * by 25 px and a tile contributes about 206 x 206 of its 256 x 256 prediction; the result is bit-identical. */
+ * (labels_only != 0), whose only U-Net output is the stitched label map, the last layers (decoder levels 0 and 1)
+ * skip the 16x16 blocks that lie entirely in the part of a tile the stitcher (src/image_tools.py:188-252) never takes,
+ * widened by each layer's dependency margin -- the tiles overlap by 25 px and a tile contributes about 206 x 206 of its
+ * 256 x 256 prediction; the result is bit-identical. */
 int ecseg_unet_work(int h, int w, int labels_only, double* flops_reference, double* flops_executed);
 
-/* Which blocks of U-Net layer `layer` (19 up1, 20 conv1-3, 21 conv1-4, 22 head; ecseg_b200.spec.UNET_LAYERS) the
+/* Which blocks of U-Net layer `layer` (16 up2, 17 conv2-3, 18 conv2-4, 19 up1, 20 conv1-3, 21 conv1-4, 22 head;
+ * ecseg_b200.spec.UNET_LAYERS) the
  * whole-image calls compute for an h x w image: mask[tile][block_row][block_col] (1 = computed), blocks being 16 x 16
  * pixels of the layer's input grid (16 x 8 for up1).  mask == NULL only returns the block grid.  Host only; lets a
  * test check the skipping against the stitcher's ownership map (src/image_tools.py:188-252) without a GPU. */

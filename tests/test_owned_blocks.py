@@ -15,6 +15,20 @@ from oracle import metaseg_oracle as mo
 
 SHAPES = [(256, 256), (300, 330), (462, 470), (1040, 1392), (2048, 2048), (2048, 2049), (700, 512), (256, 700)]
 LAYERS = {22: (0, 16, 16), 21: (1, 16, 16), 20: (2, 16, 16), 19: (3, 32, 16)}     # margin, block rows / cols in OUTPUT pixels
+LEVEL1 = {18: (0, 16, 16), 17: (1, 16, 16), 16: (2, 32, 16)}                      # margin around R1 on the 128-px grid
+
+
+def grow(mask, margin):
+    """Every pixel within `margin` (Chebyshev) of a set pixel."""
+    if not margin:
+        return mask
+    n = mask.shape[0]
+    pad = np.pad(mask, margin)
+    out = np.zeros_like(mask)
+    for dy in range(2 * margin + 1):
+        for dx in range(2 * margin + 1):
+            out |= pad[dy:dy + n, dx:dx + n]
+    return out
 
 
 def owner_map(h, w):
@@ -57,6 +71,31 @@ def test_no_needed_pixel_is_skipped(shape):
                 need = mine
             blocks = need.reshape(256 // br, br, 256 // bc, bc).any(axis=(1, 3))
             assert not (blocks & (m[t] == 0)).any(), (shape, layer, t)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_level1_blocks_cover_what_up1_reads(shape):
+    """Decoder level 1 (128-px grid).  up1 is a stride-2 transposed conv, out[2i + k] += in[i] * K[k] (k = 0..2, cropped
+    to 256): for its output to be valid on owned +-3 it reads conv2-4 at R1 = { i : {2i, 2i+1, 2i+2} meets owned +-3 },
+    conv2-4 reads conv2-3 on R1 +-1, conv2-3 reads up2 on R1 +-2."""
+    h, w = shape
+    own, pos = owner_map(h, w)
+    masks = {li: mask_of(h, w, li) for li in LEVEL1}
+    for t, (r0, c0) in enumerate(pos):
+        need0 = grow(own[r0:r0 + 256, c0:c0 + 256] == t, 3)          # up1's output, 256-px grid
+        r1 = np.zeros((128, 128), bool)
+        ys, xs = np.nonzero(need0)
+        for ky in range(3):
+            for kx in range(3):
+                yy, xx = ys - ky, xs - kx
+                ok = (yy >= 0) & (xx >= 0) & (yy % 2 == 0) & (xx % 2 == 0)
+                r1[yy[ok] // 2, xx[ok] // 2] = True
+        for li, (margin, br, bc) in LEVEL1.items():
+            need = grow(r1, margin)
+            blocks = need.reshape(128 // br, br, 128 // bc, bc).any(axis=(1, 3))
+            m = masks[li][t]
+            assert m.shape == blocks.shape
+            assert not (blocks & (m == 0)).any(), (shape, li, t)
 
 
 def test_skipping_is_substantial_but_bounded():
