@@ -53,7 +53,7 @@ __host__ __device__ constexpr int a_bytes(int nacc) { return 18 * halo_pitch(nac
 __host__ __device__ constexpr int a_stride(int nacc) { return (a_bytes(nacc) + 1023) / 1024 * 1024; }   // stage footprint
 constexpr int kOutStage = 128 * 128;               // staging tile: 128 pixels x 64 channels x 2 B
 constexpr int kPoolStage = 32 * 128;               // pooled staging tile: 32 pixels x 64 channels
-constexpr int kMaxBars = 32;
+constexpr int kMaxBars = 48;
 constexpr int kMaxCout = 1024;
 
 // conv1-1 fused into conv1-2 (FUSE1): instead of a TMA load, a halo stage is PRODUCED in place by four extra warps.
@@ -745,12 +745,15 @@ int launch_impl(ecseg_ctx* ctx, ConvTcParams& p, cudaStream_t st) {
   const int budget = 227 * 1024;
   p.a_stages = ((N_TILE == 64 && NACC == 1 && !FUSE1) || NACC == 4) ? 3 : 2;
   if (NACC == 4 && p.b_resident) p.a_stages = 2;      // room for all of the layer's view stages
+  if (NACC == 1 && p.b_resident && p.cin_chunks == 2) p.a_stages = 2;     // conv1-3: 18 resident tap tiles
   p.b_stages = (budget - smem_bytes(N_TILE, NACC, PAIR, p.a_stages, 0, FUSE1)) / b_stage_bytes(N_TILE, NACC, PAIR);
-  // resident weights: conv -- one stage per tap (Cin = 64, one output chunk); transposed conv -- one stage per
-  // (64-channel chunk, halo view), at most 8 (Cin <= 128, one output chunk)
-  const int need = NACC == 1 ? 9 : 4 * p.cin_chunks;
-  if (p.b_resident && ((FUSE1 && !PAIR) || (NACC == 1 && p.cin_chunks != 1) || p.n_chunks != 1 || p.b_stages < need || need > 9)) {
+  // resident weights: conv -- one stage per (64-channel chunk, tap) (Cin <= 128, one output chunk); transposed conv --
+  // one stage per (64-channel chunk, halo view), at most 8 (Cin <= 128, one output chunk)
+  const int need = NACC == 1 ? 9 * p.cin_chunks : 4 * p.cin_chunks;
+  if (p.b_resident && ((FUSE1 && !PAIR) || (NACC == 1 && p.cin_chunks > 2) || p.n_chunks != 1 || p.b_stages < need || need > 18)) {
     p.b_resident = 0;
+    if (NACC == 1) p.a_stages = (N_TILE == 64 && !FUSE1) ? 3 : 2;
+    if (NACC == 1) p.b_stages = (budget - smem_bytes(N_TILE, NACC, PAIR, p.a_stages, 0, FUSE1)) / b_stage_bytes(N_TILE, NACC, PAIR);
     if (NACC == 4) {
       p.a_stages = 3;
       p.b_stages = (budget - smem_bytes(N_TILE, NACC, PAIR, p.a_stages, 0, FUSE1)) / b_stage_bytes(N_TILE, NACC, PAIR);

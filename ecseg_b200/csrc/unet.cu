@@ -877,8 +877,12 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
       p.trace = ctx->trace;
     }
   }
-  // weights resident in shared memory for the whole kernel: conv1-2, conv1-4 (Cin = 64) and up1 (Cin = 128, 64 outputs)
-  p.b_resident = (((!l.convT && l.cin == 64) || (l.convT && l.cin <= 128 && !getenv("ECSEG_NO_RESIDENT_UP"))) && rows == n_tile &&
+  // weights resident in shared memory for the whole kernel: conv1-2, conv1-4 (Cin = 64), conv1-3 and up1 (Cin = 128, 64 outputs)
+  // (conv1-3, Cin = 128: its 18 tap tiles -- 72 KB per CTA of a pair -- fit next to two halo stages; resident, the
+  //  layer runs 662 -> 568 us and the step +1.3 %, profiles/r02_exp_owned_blocks.txt; ECSEG_STREAM_CONV13=1 for A/B.
+  //  The launcher clears the request where the tiles do not fit: conv2-2 / conv2-4.)
+  static const bool stream13 = getenv("ECSEG_STREAM_CONV13") != nullptr;
+  p.b_resident = (((!l.convT && (l.cin == 64 || (l.cin == 128 && !stream13))) || (l.convT && l.cin <= 128 && !getenv("ECSEG_NO_RESIDENT_UP"))) && rows == n_tile &&
                   !getenv("ECSEG_NO_RESIDENT_B")) ? 1 : 0;
   if (fuse1) {
     p.first_src = net->in_tiles ? net->in_tiles : net->in_pre;
