@@ -1,7 +1,7 @@
 #!/bin/bash
-# experiment: conv1-3 (Cin = 128) with its 18 weight tap tiles resident in shared memory (ECSEG_RESIDENT_CONV13=1)
+# A/B: conv1-3 (Cin = 128) with its 18 weight tap tiles resident in shared memory (default) vs streamed (ECSEG_STREAM_CONV13=1)
 mkdir -p gpurun_out
-ECSEG_RESIDENT_CONV13=1 timeout 900 python -m pytest tests/test_gpu_unet.py tests/test_gpu_example.py -m gpu -x -q 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_unet.py tests/test_gpu_example.py -m gpu -x -q 2>&1 | tail -3
 line() {
 python - "$1" "$2" <<'PY'
 import json, sys
@@ -11,12 +11,12 @@ PY
 }
 B="python bench.py --no-extras --artifact-images 0 --no-cpu-baseline --steps 12 --stage-images 32"
 for rep in 1 2 3; do
-  ECSEG_RESIDENT_CONV13=1 timeout 300 $B > gpurun_out/res13_on_$rep.json 2>/dev/null; line gpurun_out/res13_on_$rep.json "conv1-3 weights resident rep $rep"
-  timeout 300 $B > gpurun_out/res13_off_$rep.json 2>/dev/null; line gpurun_out/res13_off_$rep.json "conv1-3 weights streamed  rep $rep"
+  timeout 300 $B > gpurun_out/res13_on_$rep.json 2>/dev/null; line gpurun_out/res13_on_$rep.json "conv1-3 weights resident rep $rep"
+  ECSEG_STREAM_CONV13=1 timeout 300 $B > gpurun_out/res13_off_$rep.json 2>/dev/null; line gpurun_out/res13_off_$rep.json "conv1-3 weights streamed  rep $rep"
 done
 Bn="python bench.py --steps 1 --warmup 3 --images-per-step 1 --contexts 1 --artifact-images 0 --stage-images 2 --no-cpu-baseline --no-extras"
 for V in 1 0; do
-  if [ $V = 1 ]; then export ECSEG_RESIDENT_CONV13=1; else unset ECSEG_RESIDENT_CONV13; fi
+  if [ $V = 0 ]; then export ECSEG_STREAM_CONV13=1; else unset ECSEG_STREAM_CONV13; fi
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_conv_tc|k_head_tc" -s 22 -c 22 --csv --log-file gpurun_out/res13_l_$V.csv $Bn > /dev/null 2>&1
   python - $V <<'PY'
 import csv, sys
