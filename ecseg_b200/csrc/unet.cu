@@ -56,7 +56,7 @@ const Wire kWires[23] = {
 
 }  // namespace
 
-struct WorkLists;      // work lists of the level-0 decoder chain for the current image shape (below)
+struct WorkLists;      // work lists of the listed decoder layers, a few recently seen image shapes (below)
 
 struct UNet {
   WorkLists* work_lists = nullptr;
@@ -594,16 +594,30 @@ static OwnedBlocks chain_owned(const TileGrid& g, int li) {
 // only) uses the slice [off[t0], off[t1]) with the item indices rebased to its first tile.  A layer with several
 // output-channel chunks (up2) lists chunk 0's items for every tile, then chunk 1's: it is never sub-batched.  Kept on
 // the device until the shape changes.
-struct WorkLists {
+struct ShapeLists {
   int h = 0, w = 0;
+  unsigned long long stamp = 0;
   int* d[kNumListed] = {};                              // layers kFirstListed .. 22
   std::vector<int> off[kNumListed];                     // per layer: n_tiles + 1 offsets (single-chunk layers)
   std::vector<int> host[kNumListed];
 };
+// The lists of the last few image shapes a context has seen (a folder of mixed sizes alternates between a handful):
+// `cur` is the entry build_work_lists selected for the forward in flight.
+struct WorkLists {
+  static constexpr int kShapes = 4;
+  ShapeLists shape[kShapes];
+  ShapeLists* cur = nullptr;
+  unsigned long long stamp = 0;
+};
 
-static int build_work_lists(ecseg_ctx* ctx, WorkLists& wl, const TileGrid& g, cudaStream_t st) {
-  if (wl.h == g.h && wl.w == g.w) return ECSEG_OK;
-  ECSEG_CUDA(cudaStreamSynchronize(st));                 // (a previous image of another shape may still read the old lists)
+static int build_work_lists(ecseg_ctx* ctx, WorkLists& cache, const TileGrid& g, cudaStream_t st) {
+  for (auto& s : cache.shape)
+    if (s.h == g.h && s.w == g.w) { s.stamp = ++cache.stamp; cache.cur = &s; return ECSEG_OK; }
+  ShapeLists* lru = &cache.shape[0];
+  for (auto& s : cache.shape) if (s.stamp < lru->stamp) lru = &s;
+  ShapeLists& wl = *lru;
+  if (wl.h) ECSEG_CUDA(cudaStreamSynchronize(st));       // (an image of the evicted shape may still read its lists)
+  wl.h = 0; wl.w = 0; cache.cur = nullptr;
   for (int k = 0; k < kNumListed; ++k) {
     const int li = kFirstListed + k;
     const LayerDef& l = kLayers[li];
@@ -611,7 +625,7 @@ static int build_work_lists(ecseg_ctx* ctx, WorkLists& wl, const TileGrid& g, cu
     const int bcols = in_hw / (l.convT ? 8 : 16), brows = in_hw / 16;
     const int n_chunks = l.convT ? l.cout / 64 : (l.cout + 127) / 128;      // (the variant table of run_layer_tc)
     const OwnedBlocks ob = chain_owned(g, li);
-    if (!ob.on) { wl.h = 0; wl.w = 0; return ECSEG_E_STATE; }      // (caller falls back to computing everything)
+    if (!ob.on) return ECSEG_E_STATE;      // (caller falls back to computing everything)
     std::vector<int>& v = wl.host[k];
     v.clear();
     wl.off[k].assign(g.n() + 1, 0);
@@ -642,7 +656,8 @@ static int build_work_lists(ecseg_ctx* ctx, WorkLists& wl, const TileGrid& g, cu
     ECSEG_CUDA(cudaMalloc(&wl.d[k], std::max<size_t>(v.size(), 1) * sizeof(int)));
     ECSEG_CUDA(cudaMemcpy(wl.d[k], v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice));
   }
-  wl.h = g.h; wl.w = g.w;
+  wl.h = g.h; wl.w = g.w; wl.stamp = ++cache.stamp;
+  cache.cur = &wl;
   return ECSEG_OK;
 }
 
@@ -666,7 +681,8 @@ int unet_owned_mask(int h, int w, int layer, uint8_t* mask, int* rows, int* cols
 static WorkLists* new_work_lists() { return new WorkLists(); }
 static void free_work_lists(WorkLists* wl) {
   if (!wl) return;
-  for (auto& d : wl->d) if (d) cudaFree(d);
+  for (auto& s : wl->shape)
+    for (auto& d : s.d) if (d) cudaFree(d);
   delete wl;
 }
 
@@ -786,9 +802,10 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
     if (skip_unowned) {
       const int rc = build_work_lists(ctx, *net->work_lists, *grid, st);
       if (rc == ECSEG_OK) {
-        const std::vector<int>& off = net->work_lists->off[22 - kFirstListed];
+        const ShapeLists& sl = *net->work_lists->cur;
+        const std::vector<int>& off = sl.off[22 - kFirstListed];
         if (off[tile0 + n] == off[tile0]) return ECSEG_OK;       // no owned pixel in these tiles
-        h.work = net->work_lists->d[22 - kFirstListed] + off[tile0]; h.n_work = off[tile0 + n] - off[tile0];
+        h.work = sl.d[22 - kFirstListed] + off[tile0]; h.n_work = off[tile0 + n] - off[tile0];
         h.work_base = tile0 * (kTile / 16) * (kTile / 16);
       } else if (rc != ECSEG_E_STATE) return rc;
     }
@@ -859,10 +876,11 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   if (skip_unowned) {
     const int rc = build_work_lists(ctx, *net->work_lists, *grid, st);
     if (rc == ECSEG_OK) {
-      const std::vector<int>& off = net->work_lists->off[li - kFirstListed];
+      const ShapeLists& sl = *net->work_lists->cur;
+      const std::vector<int>& off = sl.off[li - kFirstListed];
       if (off[tile0] < 0 || off[tile0 + n] < 0) { ctx->err = "unet: a multi-chunk work list cannot be sliced by tile"; return ECSEG_E_STATE; }
       if (off[tile0 + n] == off[tile0]) return ECSEG_OK;         // nothing downstream reads these tiles' blocks
-      p.work = net->work_lists->d[li - kFirstListed] + off[tile0]; p.n_work = off[tile0 + n] - off[tile0];
+      p.work = sl.d[li - kFirstListed] + off[tile0]; p.n_work = off[tile0 + n] - off[tile0];
       p.work_base = tile0 * ((in_hw / 16) * (in_hw / (l.convT ? 8 : 16)) / 2);   // pair items per tile
     } else if (rc != ECSEG_E_STATE) return rc;
   }
