@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(FUSE1 ? kThreads + kGenThreads : kThreads, 1) 
   };
   // pipeline trace of CTA 0: role r stamps its k-th item at point s
   auto stamp = [&](int role, int k, int sidx) {
-    if (p.trace && blockIdx.x == 0 && k < kTraceItems) p.trace[(role * kTraceItems + k) * 4 + sidx] = clock64();
+    if (p.trace && blockIdx.x == 0 && !(k & ((1 << p.trace_shift) - 1)) && (k >> p.trace_shift) < kTraceItems)
+      p.trace[(role * kTraceItems + (k >> p.trace_shift)) * 4 + sidx] = clock64();
   };
   const int bw = p.W / kBlkW, bh = p.H >> 4;
   const int n_mblocks = p.n_img * bh * bw;

@@ -72,6 +72,7 @@ struct ConvTcParams {
   int work_base;          // subtracted from a list entry's item index (the list indexes the whole image, a launch a sub-batch)
   int* progress;          // Counters::progress (nullable): role progress markers of CTA 0 for ecseg_debug_progress
   long long* trace;       // nullable: clock64 stamps of CTA 0, [role kTraceRoles][item kTraceItems][stamp 4] (ecseg_debug_trace)
+  int trace_shift;        // every 2^trace_shift-th item of a role is stamped (ECSEG_TRACE_STRIDE_LOG2; 0 = the first kTraceItems)
   // conv1-1 fused in front of this layer (conv1-2 only; first_src == nullptr: off).  The halo stages are then computed
   // in the kernel from the uint8 input (materialised tiles, or the pre-processed image through the tile grid) and
   // tm_a is unused.

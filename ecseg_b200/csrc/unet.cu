@@ -893,6 +893,7 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
       if (!ctx->trace) ECSEG_CUDA(cudaMalloc((void**)&ctx->trace, kTraceRoles * kTraceItems * 4 * sizeof(long long)));
       ECSEG_CUDA(cudaMemsetAsync(ctx->trace, 0, kTraceRoles * kTraceItems * 4 * sizeof(long long), st));
       p.trace = ctx->trace;
+      if (const char* s = getenv("ECSEG_TRACE_STRIDE_LOG2")) p.trace_shift = std::max(0, std::min(8, atoi(s)));
     }
   }
   // weights resident in shared memory for the whole kernel: conv1-2, conv1-4 (Cin = 64), conv1-3 and up1 (Cin = 128, 64 outputs)

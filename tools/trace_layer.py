@@ -24,6 +24,26 @@ for li in layers:
     t = buf.reshape(R, K, 4).astype(np.float64)
     t0 = t[t > 0].min()
     t = np.where(t > 0, t - t0, np.nan)
+    shift = int(os.environ.get("ECSEG_TRACE_STRIDE_LOG2", "0"))
+    if shift:            # sparse trace of the whole kernel: every 2^shift-th item, the period over windows of the kernel
+        done = t[1, :, 3]
+        n = int(np.sum(~np.isnan(done)))
+        print(f"=== layer {li} ({spec.UNET_LAYERS[li][0]}): every {1 << shift}-th item of CTA 0, {n} samples; MMA issue-done period per item")
+        per = np.diff(done[:n]) / (1 << shift)
+        print("  item: " + " ".join(f"{(j + 1) << shift:6d}" for j in range(n - 1)))
+        print("period: " + " ".join(f"{v:6.0f}" for v in per))
+        print(f"  whole kernel (first stamp -> last epilogue hand-back): {np.nanmax(t):.0f} cycles; mean period {np.nanmean(per):.0f}")
+        for g in (2, 3):
+            w = t[g, :n, 1] - t[g, :n, 0]; work = t[g, :n, 2] - t[g, :n, 1]
+            print(f"  {names[g]} wait accumulators: " + " ".join(f"{v:6.0f}" for v in w))
+            print(f"  {names[g]} work:              " + " ".join(f"{v:6.0f}" for v in work))
+        if not np.all(np.isnan(t[4])):
+            g = t[4, :n]; h = t[5, :n]
+            print("  gen wait:           " + " ".join(f"{v:6.0f}" for v in g[:, 1] - g[:, 0]))
+            print("  gen build:          " + " ".join(f"{v:6.0f}" for v in g[:, 2] - g[:, 1]))
+            print("  gen read-back+store:" + " ".join(f"{v:6.0f}" for v in h[:, 2] - g[:, 2]))
+            print("  gen issue+signal:   " + " ".join(f"{v:6.0f}" for v in g[:, 3] - h[:, 2]))
+        continue
     print(f"=== layer {li} ({spec.UNET_LAYERS[li][0]}): cycles relative to the first stamp; items 8..19 of CTA 0")
     roles = [r for r in range(R) if not np.all(np.isnan(t[r]))]
     for k in range(8, 20):
