@@ -235,7 +235,8 @@ int head_tc_launch(ecseg_ctx* ctx, const HeadTcParams& p, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = getenv("ECSEG_PDL") ? 1 : 0;     // opt-in, see conv_tc.cu
+  static const bool pdl = getenv("ECSEG_PDL") != nullptr;     // opt-in, see conv_tc.cu
+  cfg.numAttrs = pdl ? 1 : 0;
   ECSEG_CUDA(cudaLaunchKernelEx(&cfg, k_head_tc, p));
   ECSEG_CHECK_LAUNCH();
   return ECSEG_OK;

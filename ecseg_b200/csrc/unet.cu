@@ -78,6 +78,14 @@ struct UNet {
   const uint8_t* in_pre = nullptr;
   int skip_unowned = 1;               // skip blocks in the unowned tile margin in the labels-only path (ECSEG_NO_OWNER_SKIP=1: off)
   int l0_subbatch = 0;                // tiles per sub-batch of the level-0 decoder chain (0 = whole batch; ECSEG_L0_SUBBATCH)
+  // debug / A-B switches read from the environment once per forward (unet_forward), not once per layer:
+  // tests and tools/trace_layer.py change some of them between two forwards of one process
+  struct Knobs {
+    int trace_layer = -1, trace_shift = 0;    // ECSEG_TRACE_LAYER, ECSEG_TRACE_STRIDE_LOG2
+    bool table_v1 = false;                    // ECSEG_TC_TABLE_V1: the round-1 per-layer variant table
+    bool fuse1_single = false;                // ECSEG_FUSE1_SINGLE: fused first layer as single CTAs
+    bool no_resident_up = false, no_resident_b = false, stream13 = false;   // ECSEG_NO_RESIDENT_UP / _B, ECSEG_STREAM_CONV13
+  } knobs;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -825,13 +833,13 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   int n_tile = l.convT ? 64 : (rows < 128 ? rows : 128);
   int cs = 3;
   if (li == 8 || li == 9) n_tile = 256;             // conv5-1, conv5-2
-  if (getenv("ECSEG_TC_TABLE_V1") && (li == 1 || li == 2 || li == 19)) cs = 2;   // the round-1 table, for A/B runs
+  if (net->knobs.table_v1 && (li == 1 || li == 2 || li == 19)) cs = 2;   // the round-1 table, for A/B runs
   if (net->tc_ntile_max > 0 && !l.convT) n_tile = rows < net->tc_ntile_max ? rows : net->tc_ntile_max;   // debug override
   if (net->tc_cluster > 0) cs = net->tc_cluster;                                                      // debug override
   const bool fuse1 = li == 1 && net->fuse_first && net->stop_after != 0 && net->tc_cluster == 0 && net->tc_ntile_max == 0;
   // the fused conv1-1 -> conv1-2 kernel runs as CTA pairs too (a single CTA's N = 64 MMA takes ~85 cycles: the layer
   // was MMA-paced at 31 % tensor activity); ECSEG_FUSE1_SINGLE=1 selects the single-CTA variant for A/B runs
-  if (fuse1) cs = getenv("ECSEG_FUSE1_SINGLE") ? 1 : 3;
+  if (fuse1) cs = net->knobs.fuse1_single ? 1 : 3;
   const size_t pin = kBufs[wr.in].ch, pout = kBufs[wr.out].ch;
   // halo box: 18 rows x (block width + 2) pixels; transposed convolutions work on 16x8 blocks (conv_tc.cu: blk_w)
   ECSEG_TRY(make_tm_nhwc(ctx, &p.tm_a, tile_base(wr.in, in_hw), l.cin, in_hw, in_hw, NT, pin, pin * in_hw, pin * in_hw * in_hw,
@@ -888,21 +896,19 @@ static int run_layer_tc(ecseg_ctx* ctx, int li, int n, float* d_probs, float* d_
   p.act_overflow = &ctx->counters->act_overflow;
   p.layer_id = li + 1;
   p.progress = ctx->counters->progress;
-  if (const char* e = getenv("ECSEG_TRACE_LAYER")) {       // pipeline trace of one layer (tools/trace_layer.py)
-    if (atoi(e) == li) {
-      if (!ctx->trace) ECSEG_CUDA(cudaMalloc((void**)&ctx->trace, kTraceRoles * kTraceItems * 4 * sizeof(long long)));
-      ECSEG_CUDA(cudaMemsetAsync(ctx->trace, 0, kTraceRoles * kTraceItems * 4 * sizeof(long long), st));
-      p.trace = ctx->trace;
-      if (const char* s = getenv("ECSEG_TRACE_STRIDE_LOG2")) p.trace_shift = std::max(0, std::min(8, atoi(s)));
-    }
+  if (net->knobs.trace_layer == li) {                     // pipeline trace of one layer (tools/trace_layer.py)
+    if (!ctx->trace) ECSEG_CUDA(cudaMalloc((void**)&ctx->trace, kTraceRoles * kTraceItems * 4 * sizeof(long long)));
+    ECSEG_CUDA(cudaMemsetAsync(ctx->trace, 0, kTraceRoles * kTraceItems * 4 * sizeof(long long), st));
+    p.trace = ctx->trace;
+    p.trace_shift = net->knobs.trace_shift;
   }
   // weights resident in shared memory for the whole kernel: conv1-2, conv1-4 (Cin = 64), conv1-3 and up1 (Cin = 128, 64 outputs)
   // (conv1-3, Cin = 128: its 18 tap tiles -- 72 KB per CTA of a pair -- fit next to two halo stages; resident, the
   //  layer runs 662 -> 568 us and the step +1.3 %, profiles/r02_exp_owned_blocks.txt; ECSEG_STREAM_CONV13=1 for A/B.
   //  The launcher clears the request where the tiles do not fit: conv2-2 / conv2-4.)
-  static const bool stream13 = getenv("ECSEG_STREAM_CONV13") != nullptr;
-  p.b_resident = (((!l.convT && (l.cin == 64 || (l.cin == 128 && !stream13))) || (l.convT && l.cin <= 128 && !getenv("ECSEG_NO_RESIDENT_UP"))) && rows == n_tile &&
-                  !getenv("ECSEG_NO_RESIDENT_B")) ? 1 : 0;
+  const UNet::Knobs& kn = net->knobs;
+  p.b_resident = (((!l.convT && (l.cin == 64 || (l.cin == 128 && !kn.stream13))) || (l.convT && l.cin <= 128 && !kn.no_resident_up)) &&
+                  rows == n_tile && !kn.no_resident_b) ? 1 : 0;
   if (fuse1) {
     p.first_src = net->in_tiles ? net->in_tiles : net->in_pre;
     p.first_from_tiles = net->in_tiles != nullptr;
@@ -921,6 +927,17 @@ int unet_forward(ecseg_ctx* ctx, const uint8_t* d_tiles, const uint8_t* d_pre, c
   if (!d_tiles && !(d_pre && grid)) { ctx->err = "unet_forward: no input"; return ECSEG_E_INVALID; }
   if (d_labels && !grid) { ctx->err = "unet_forward: fused stitch needs the tile grid"; return ECSEG_E_INVALID; }
   const int prec = net->precision;
+  {
+    UNet::Knobs kn;
+    if (const char* e = getenv("ECSEG_TRACE_LAYER")) kn.trace_layer = atoi(e);
+    if (const char* e = getenv("ECSEG_TRACE_STRIDE_LOG2")) kn.trace_shift = std::max(0, std::min(8, atoi(e)));
+    kn.table_v1 = getenv("ECSEG_TC_TABLE_V1") != nullptr;
+    kn.fuse1_single = getenv("ECSEG_FUSE1_SINGLE") != nullptr;
+    kn.no_resident_up = getenv("ECSEG_NO_RESIDENT_UP") != nullptr;
+    kn.no_resident_b = getenv("ECSEG_NO_RESIDENT_B") != nullptr;
+    kn.stream13 = getenv("ECSEG_STREAM_CONV13") != nullptr;
+    net->knobs = kn;
+  }
   if (d_labels) ECSEG_CUDA(cudaMemsetAsync(d_labels, 0, (size_t)grid->h * grid->w, st));  // never-written strips -> 0
   net->in_tiles = d_tiles; net->in_pre = d_pre;
   const bool fused_first = prec != ECSEG_PREC_FP32 && net->fuse_first && net->stop_after != 0 && net->tc_cluster == 0 &&
