@@ -23,7 +23,7 @@ import numpy as np
 from .spec import BN_EPS, NUM_CLASSES, UNET_LAYERS
 
 # seed -> (per-class gain on the final kernel, per-class offset injected through the constant
-# hidden channel).  Produced once by tools/calibrate_head.py with the CPU oracle on
+# hidden channel).  Produced once by tests/devtools/calibrate_head.py with the CPU oracle on
 # synth.synth_dapi(seed=1000, 512x512); frozen here so every machine builds bit-identical weights.
 HEAD_CALIBRATION = {
     (0, True): ([2.9478561878204346, 1.082884669303894, 1.4067955017089844, 1.6996512413024902],

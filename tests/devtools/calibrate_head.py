@@ -1,14 +1,14 @@
 #!/usr/bin/env python3
 """One-off: fit the classification-head gains/offsets frozen in ecseg_b200/weights.py
 (HEAD_CALIBRATION) so that random-init weights give all four classes on synthetic DAPI.
-Uses the CPU oracle U-Net; run in the development container:  python tools/calibrate_head.py"""
+Uses the CPU oracle U-Net; run in the development container:  python tests/devtools/calibrate_head.py"""
 import os
 import sys
 import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from ecseg_b200 import synth, weights as wmod  # noqa: E402
 from oracle import metaseg_oracle as mo  # noqa: E402
 from oracle.unet_oracle import UNetOracle  # noqa: E402

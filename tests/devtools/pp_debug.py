@@ -1,7 +1,7 @@
 """Localise a post-processing mismatch: every step of meta_inference on the GPU against the oracle, on the oracle's own
 intermediate maps, for the small ragged cases of tests/test_gpu_postproc.py.  Run plain and under compute-sanitizer."""
 import os, sys, warnings
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from ecseg_b200 import synth
 from ecseg_b200.engine import Engine

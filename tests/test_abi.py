@@ -59,12 +59,15 @@ def test_no_gpu_means_loud_failure(lib):
 
 
 def test_product_never_imports_oracle():
-    for dirpath, _d, files in os.walk(os.path.join(ROOT, "ecseg_b200")):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                txt = open(os.path.join(dirpath, f)).read()
-                assert not re.search(r"^\s*(from|import)\s+oracle|oracle\.[a-z_]+|oracle/|import_module\(.oracle", txt, re.M), \
-                    os.path.join(dirpath, f)
+    """The oracle is test infrastructure: nothing in the package, the drop-in scripts, the C ABI header or the
+    measurement / profiling helpers under tools/ imports or executes it (helpers that need it live in tests/devtools/)."""
+    for top in ("ecseg_b200", "src", "include", "tools"):
+        for dirpath, _d, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+                    txt = open(os.path.join(dirpath, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle|oracle\.[a-z_]+|oracle/|import_module\(.oracle", txt, re.M), \
+                        os.path.join(dirpath, f)
 
 
 def test_flops_and_blob_size():
