@@ -12,6 +12,11 @@ pytestmark = pytest.mark.gpu
 LOGIT_REL_TOL_FP32 = 1e-3
 LABEL_AGREEMENT = 0.999
 BF16_FLOOR = 0.995
+# GPU against the CPU restatement of its own arithmetic (UNetOracle16), rms error relative to the layer's scale, for the
+# first tensor-core layer (fused conv1-1 + conv1-2), where the two can only differ by rounding flips caused by the
+# order of the fp32 accumulation: measured 3.0e-5 in fp16 (a tenth of the distance to the fp32 oracle).  Further down
+# the rounding decisions of the two decorrelate (9e-5, 1.9e-4, ... 7e-4) and the general bars apply.
+BAR16_FIRST = {"fp16": 1e-4, "bf16": 8e-4}
 
 
 @pytest.fixture(scope="module")
@@ -82,32 +87,51 @@ def test_every_layer_against_the_oracle(setup, prec):
     / 2x what 16-bit operands with fp32 accumulation cost in an emulation on the CPU (fp16: max <= 1.4e-3, rms
     <= 9.2e-4; bf16: 1.1e-2, 7.9e-3); a wrong block, tap or channel chunk in any layer is an O(1) error."""
     from ecseg_b200 import spec
-    from oracle.unet_oracle import UNetOracle
+    from oracle.unet_oracle import UNetOracle, UNetOracle16
     s = setup
     eng = s["eng"]
     tiles = s["tiles"]
     n = len(tiles)
-    taps = {}
+    x = torch.from_numpy(np.ascontiguousarray(tiles)).float().permute(0, 3, 1, 2)
+    taps, taps16 = {}, {}
     with torch.no_grad():
-        UNetOracle(s["w"], batch=n).logits(torch.from_numpy(np.ascontiguousarray(tiles)).float().permute(0, 3, 1, 2), taps)
+        UNetOracle(s["w"], batch=n).logits(x, taps)
+        UNetOracle16(s["w"], torch.float16 if prec == "fp16" else torch.bfloat16).logits(x, taps16)
     bar_max, bar_rms = (4e-3, 2e-3) if prec == "fp16" else (3e-2, 1.6e-2)
     eng.load_weights(s["w"], prec)
-    worst = (0.0, 0.0)
+    worst, worst16 = [0.0, 0.0], [0.0, 0.0]
+
+    def errs(got, ref):
+        return (float(np.abs(got - ref).max() / np.abs(ref).max()),
+                float(np.sqrt(np.mean((got - ref) ** 2)) / np.sqrt(np.mean(ref ** 2))))
+
     try:
         for li in range(1, 22):                  # conv1-1 is fused into conv1-2 (its activation never exists); 22 = logits
+            name = spec.UNET_LAYERS[li][0]
             eng.debug_set(stop_after=li)
             eng.unet_forward(tiles[..., 0])
             got = eng.layer_output(li, n).cpu().numpy()
-            ref = taps[spec.UNET_LAYERS[li][0]].permute(0, 2, 3, 1).numpy()
+            ref = taps[name].permute(0, 2, 3, 1).numpy()
             assert got.shape == ref.shape
-            e_max = float(np.abs(got - ref).max() / np.abs(ref).max())
-            e_rms = float(np.sqrt(np.mean((got - ref) ** 2)) / np.sqrt(np.mean(ref ** 2)))
-            worst = (max(worst[0], e_max), max(worst[1], e_rms))
-            assert e_max <= bar_max and e_rms <= bar_rms, (spec.UNET_LAYERS[li][0], e_max, e_rms)
+            e_max, e_rms = errs(got, ref)
+            assert e_max <= bar_max and e_rms <= bar_rms, (name, e_max, e_rms)
+            # against the same arithmetic restated on the CPU: only the fp32 accumulation order differs, which shows
+            # where a stored activation sits on a rounding boundary of the 16-bit format
+            f_max, f_rms = errs(got, taps16[name].permute(0, 2, 3, 1).numpy())
+            assert f_max <= bar_max and f_rms <= (BAR16_FIRST[prec] if li == 1 else bar_rms), (name, f_max, f_rms)
+            worst = [max(worst[0], e_max), max(worst[1], e_rms)]
+            worst16 = [max(worst16[0], f_max), max(worst16[1], f_rms)]
+            print(f"  {name:8s} vs fp32 oracle {e_max:.2e} / {e_rms:.2e}   vs 16-bit-arithmetic oracle {f_max:.2e} / {f_rms:.2e}")
         assert eng.device_error() == 0
     finally:
         eng.debug_set(stop_after=-1)
-    print(f"{prec}: worst layer max err {worst[0]:.3e}, rms err {worst[1]:.3e} (relative to the layer's scale)")
+    print(f"{prec}: worst layer against the fp32 oracle: max err {worst[0]:.3e}, rms err {worst[1]:.3e}; against the "
+          f"16-bit-arithmetic oracle: max err {worst16[0]:.3e}, rms err {worst16[1]:.3e} (relative to the layer's scale)")
+    _probs, logits = eng.unet_forward(tiles[..., 0], want_logits=True)
+    z16 = taps16["final"].permute(0, 2, 3, 1).numpy()
+    l_max, l_rms = errs(logits.cpu().numpy(), z16)
+    print(f"{prec}: logits against the 16-bit-arithmetic oracle: max err {l_max:.3e}, rms err {l_rms:.3e}")
+    assert l_max <= 2 * bar_max and l_rms <= 2 * bar_rms, (l_max, l_rms)
 
 
 @pytest.mark.xfail(reason="bf16 operands (8-bit mantissa) measure ~99.8 % < the 99.9 % label bar; fp16 -- same tcgen05 "

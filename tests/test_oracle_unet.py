@@ -89,3 +89,22 @@ def test_transposed_conv_crops_the_far_side():
     t = torch.nn.functional.conv_transpose2d(torch.from_numpy(x.transpose(2, 0, 1)[None]),
                                              torch.from_numpy(k.transpose(3, 2, 0, 1).copy()), stride=2)[0, 0, :4, :4].numpy()
     assert np.array_equal(t, out)
+
+
+def test_16bit_arithmetic_oracle_is_the_same_graph():
+    """UNetOracle16 restates the GPU's tensor-core arithmetic (BatchNorm folded as ecseg_load_weights folds it, 16-bit
+    operands, fp32 accumulation, 16-bit stores).  With the operand format set to fp32 every rounding in it is the
+    identity, so it must reproduce the fp32 oracle up to the folding's own rounding: same graph, same layouts, same
+    crops.  In fp16 / bf16 it moves away from it by what those formats cost (GPU figures: 2.1e-3 / 1.6e-2)."""
+    from oracle.unet_oracle import UNetOracle16
+    w = wmod.make_weights(0)
+    rng = np.random.default_rng(4)
+    tiles = rng.integers(0, 256, (2, 64, 48, 1), dtype=np.uint8)
+    ref = UNetOracle(w, batch=2).predict_logits(tiles)
+    scale = np.abs(ref).max()
+    same = UNetOracle16(w, torch.float32).predict_logits(tiles)
+    assert np.abs(same - ref).max() <= 2e-5 * scale
+    for fmt, lo, hi in ((torch.float16, 1e-4, 6e-3), (torch.bfloat16, 1e-3, 5e-2)):
+        z = UNetOracle16(w, fmt).predict_logits(tiles)
+        err = np.abs(z - ref).max() / scale
+        assert lo < err < hi, (fmt, err)
