@@ -16,7 +16,7 @@ BF16_FLOOR = 0.995
 # first tensor-core layer (fused conv1-1 + conv1-2), where the two can only differ by rounding flips caused by the
 # order of the fp32 accumulation: measured 3.0e-5 in fp16 (a tenth of the distance to the fp32 oracle).  Further down
 # the rounding decisions of the two decorrelate (9e-5, 1.9e-4, ... 7e-4) and the general bars apply.
-BAR16_FIRST = {"fp16": 1e-4, "bf16": 8e-4}
+BAR16_FIRST = {"fp16": 1e-4, "bf16": 4e-4}        # measured 3.0e-5 and 1.06e-4
 
 
 @pytest.fixture(scope="module")
