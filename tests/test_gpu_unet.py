@@ -247,7 +247,10 @@ def test_owned_block_skipping_equals_full_computation(shape):
     eng = Engine(0, max(h, 256), max(w, 256))
     try:
         eng.load_weights(wmod.make_weights(0), "fp16")
-        for rep in range(2):                                   # second pass: buffers hold the first pass's stale margins
+        other = synth.synth_dapi(7 + h % 5 + w % 3, h, w)
+        for rep in range(2):
+            if rep:      # second pass: every activation buffer holds ANOTHER image's values in full (first pass: zeros),
+                eng.unet_forward(eng.tile(eng.preprocess(other)[0]))     # so a block skipped by mistake reads wrong data
             labels, n_ec, ec_px = eng.segment_host(img)
             pre, _ = eng.preprocess(img)
             raw = eng.stitch_argmax(eng.unet_forward(eng.tile(pre)), h, w)
