@@ -216,7 +216,8 @@ int ecseg_debug_progress(ecseg_ctx* ctx, int32_t out[8]);
 
 /* clock64 stamps CTA 0 of the layer named by the environment variable ECSEG_TRACE_LAYER left behind in the last
  * forward: int64 [role 6: TMA producer, MMA issuer, epilogue group 0, epilogue group 1, conv1-1 generator, generator detail][item 48][stamp 4]
- * (tools/trace_layer.py prints them as a per-item timeline).  n = number of int64 the caller's buffer holds. */
+ * (tools/trace_layer.py prints them as a per-item timeline); with ECSEG_TRACE_STRIDE_LOG2=s every 2^s-th item of a role
+ * is stamped instead of the first 48, which covers a whole kernel.  n = number of int64 the caller's buffer holds. */
 int ecseg_debug_trace(ecseg_ctx* ctx, int64_t* out, int n);
 
 /* Synchronise and read the device-side pipeline watchdog flag (0 = healthy). */
