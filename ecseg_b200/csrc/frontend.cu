@@ -115,23 +115,51 @@ __device__ void otsu_from_hist(const unsigned int* sh, int n_px, Counters* cnt) 
 // Pass 1: channel pick (channel 2 of colour images, image_tools.py:88-89), u16->u8, 256-bin histogram; the LAST
 // block to finish evaluates the Otsu threshold (no separate one-thread launch, no round trip of the histogram
 // through another kernel's global loads).
+// The block's histogram is kept in kHistCopies shared-memory copies selected by the lane (pitch 257 words: a bin's
+// copies lie in different banks).  A DAPI image is mostly background within a few grey levels, so the lanes of a warp
+// hit the same handful of bins: one copy serialises those atomics 32-fold, eight copies 4-fold.
+constexpr int kHistCopies = 8, kHistPitch = 257;
+
 template <typename T>
-__global__ void k_pre_convert_hist(const T* __restrict__ img, int n_px, int ch, uint8_t* __restrict__ pre,
-                                   Counters* __restrict__ cnt) {
-  __shared__ unsigned int sh[256];
+__global__ void __launch_bounds__(256) k_pre_convert_hist(const T* __restrict__ img, int n_px, int ch, uint8_t* __restrict__ pre,
+                                                          Counters* __restrict__ cnt) {
+  __shared__ unsigned int sh[kHistCopies * kHistPitch];
   __shared__ int s_last;
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = 0;
+  for (int i = threadIdx.x; i < kHistCopies * kHistPitch; i += blockDim.x) sh[i] = 0;
   __syncthreads();
+  unsigned int* my = sh + (threadIdx.x & (kHistCopies - 1)) * kHistPitch;
   const int pick = ch > 1 ? 2 : 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += gridDim.x * blockDim.x) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+  int done = 0;      // pixels [0, done) are covered by the vector loop
+  if (sizeof(T) == 1 && ch == 1 && ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(pre)) & 15) == 0) {
+    // single-channel uint8 (the common input): 16 pixels per thread and step, the plane is copied as it is
+    const int n_vec = n_px >> 4;
+    const uint4* src = reinterpret_cast<const uint4*>(img);
+    uint4* dst = reinterpret_cast<uint4*>(pre);
+    for (int i = tid; i < n_vec; i += nthr) {
+      const uint4 v = src[i];
+      dst[i] = v;
+      const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(&my[(w[k] >> (8 * j)) & 0xffu], 1u);
+    }
+    done = n_vec << 4;
+  }
+  for (int i = done + tid; i < n_px; i += nthr) {
     unsigned int v = img[(size_t)i * ch + pick];
     uint8_t b = sizeof(T) == 2 ? scale_u16(v) : (uint8_t)v;
     pre[i] = b;
-    atomicAdd(&sh[b], 1u);
+    atomicAdd(&my[b], 1u);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 256; i += blockDim.x)
-    if (sh[i]) atomicAdd(&cnt->hist[i], sh[i]);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    unsigned int n = 0;
+#pragma unroll
+    for (int c = 0; c < kHistCopies; ++c) n += sh[c * kHistPitch + i];
+    if (n) atomicAdd(&cnt->hist[i], n);
+  }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = atomicAdd(&cnt->pre_ticket, 1) == (int)gridDim.x - 1;
@@ -143,11 +171,26 @@ __global__ void k_pre_convert_hist(const T* __restrict__ img, int n_px, int ch, 
   otsu_from_hist(sh, n_px, cnt);
 }
 
-// Pass 2: apply the polarity flip (~img) and emit the dapi/ artefact (255 - pre, utils.py:112).
-__global__ void k_pre_apply(uint8_t* __restrict__ pre, uint8_t* __restrict__ dapi, int n_px,
-                            const Counters* __restrict__ cnt) {
+// Pass 2: apply the polarity flip (~img) and emit the dapi/ artefact (255 - pre, utils.py:112); 16 pixels per thread
+// and step where the planes are 16-byte aligned.
+__global__ void __launch_bounds__(256) k_pre_apply(uint8_t* __restrict__ pre, uint8_t* __restrict__ dapi, int n_px,
+                                                   const Counters* __restrict__ cnt) {
   const int flip = cnt->flip;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += gridDim.x * blockDim.x) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+  int done = 0;
+  if (((reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(dapi)) & 15) == 0) {      // (dapi == nullptr is aligned)
+    const int n_vec = n_px >> 4;
+    uint4* p4 = reinterpret_cast<uint4*>(pre);
+    uint4* d4 = reinterpret_cast<uint4*>(dapi);
+    if (flip || dapi)
+      for (int i = tid; i < n_vec; i += nthr) {
+        uint4 v = p4[i];
+        if (flip) { v.x = ~v.x; v.y = ~v.y; v.z = ~v.z; v.w = ~v.w; p4[i] = v; }
+        if (dapi) d4[i] = make_uint4(~v.x, ~v.y, ~v.z, ~v.w);
+      }
+    done = n_vec << 4;
+  }
+  for (int i = done + tid; i < n_px; i += nthr) {
     uint8_t v = pre[i];
     if (flip) { v = 255 - v; pre[i] = v; }
     if (dapi) dapi[i] = 255 - v;
